@@ -58,6 +58,9 @@ extern "C" {
                              /* else f64 recurrence (hard part 1)               */
 #define TFX_PREC_F32    0x1u /* force float32 recurrence (f32 I/O only)                      */
 #define TFX_PREC_F64    0x2u /* force float64 recurrence (what the reference computes in)    */
+#define TFX_NO_TMA      0x8u  /* cascade kernel choice: never / always (where eligible, see        */
+#define TFX_FORCE_TMA   0x10u /* tfx_sos_cascade_uses_tma) take the TMA-tiled kernel; neither =   */
+                              /* the library's heuristic (A/B timing, tests)                      */
 #define TFX_NO_SPLIT    0x4u /* never split a channel in time (one sequential stream per     */
                              /* channel; exact for unstable filters; used by tests)          */
 
@@ -104,6 +107,13 @@ int tfx_sos_cascade_f64(const double *x, double *y, int64_t C, int64_t T,
                         double *state_x, double *state_y,
                         uint32_t flags, void *workspace, size_t workspace_bytes,
                         void *stream);
+
+/* 1 when a call with these arguments is ELIGIBLE for the TMA-tiled kernel
+ * (cp.async.bulk.tensor tiles of 32 channels x 64 samples): enough channels to fill the
+ * lanes, 16-byte aligned rows, T < 2^31.  0: only the generic cp.async kernel applies.
+ * elem_bytes is 4 or 8.                                                                   */
+int tfx_sos_cascade_uses_tma(const void *x, const void *y, int64_t C, int64_t T,
+                             int64_t ldx, int64_t ldy, int elem_bytes);
 
 /* What TFX_PREC_AUTO resolves to for this cascade: returns TFX_PREC_F32 or TFX_PREC_F64,
  * and (optionally) the probe's estimated f32 round-off relative to max|y|.               */

@@ -1,0 +1,131 @@
+"""GPU parity of the TMA-tiled cascade kernel (sos_tma.cu) -- the path every BASELINE
+config takes (many channels, aligned rows) -- against the oracle, and A/B against the
+generic cp.async kernel (TFX_NO_TMA) on the same inputs."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import scipy.signal as sps
+import torch
+
+from conftest import rel_to_max
+from oracle import oracle
+from torchfx_b200 import _native, _ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL_F32 = 1e-5
+TOL_F64REC = 1e-6
+
+
+def uses_tma(x, y=None):
+    y = x if y is None else y
+    return bool(_native.load().tfx_sos_cascade_uses_tma(x.data_ptr(), y.data_ptr(), x.shape[0], x.shape[1], x.stride(0), y.stride(0), x.element_size()))
+
+
+def run(x_np, sos_np, sx=None, sy=None, **kw):
+    x = torch.from_numpy(np.ascontiguousarray(x_np)).to(DEV)
+    K, C = sos_np.shape[0], x.shape[0]
+    stx = torch.zeros(K, C, 2, dtype=torch.float64, device=DEV) if sx is None else torch.from_numpy(sx).to(DEV)
+    sty = torch.zeros(K, C, 2, dtype=torch.float64, device=DEV) if sy is None else torch.from_numpy(sy).to(DEV)
+    kw.setdefault("force_tma", not kw.get("no_tma", False))
+    y = _ops.sos_cascade_(x, torch.from_numpy(sos_np), stx, sty, **kw)
+    torch.cuda.synchronize()
+    return y.cpu().numpy(), stx.cpu().numpy(), sty.cpu().numpy(), x
+
+
+def test_path_selection():
+    a = torch.zeros(64, 4096, device=DEV)
+    assert uses_tma(a)
+    assert not uses_tma(torch.zeros(2, 4096, device=DEV))  # too few channels for channel-per-lane
+    assert not uses_tma(torch.zeros(64, 4099, device=DEV))  # rows not 16-byte aligned
+    assert uses_tma(torch.zeros(64, 4096, dtype=torch.float64, device=DEV))
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 4, 5, 6, 7, 8, 12])
+def test_every_section_count(K):
+    rng = np.random.default_rng(100 + K)
+    x = (0.1 * rng.standard_normal((64, 12000))).astype(np.float32)
+    sos = sps.butter(2 * K, 0.21, output="sos")
+    want, wsx, wsy = oracle.sos_cascade(x, sos)
+    for precision, tol in (("f32", TOL_F32), ("f64", TOL_F64REC)):
+        y, sx, sy, xt = run(x, sos, precision=precision)
+        assert uses_tma(xt)
+        assert rel_to_max(y, want) < tol, (K, precision)
+        np.testing.assert_allclose(sx, wsx, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(sy, wsy, rtol=1e-3, atol=tol * 10 * max(np.abs(wsy).max(), 1e-30))
+
+
+@pytest.mark.parametrize("shape", [(32, 4), (32, 8), (64, 60), (64, 64), (64, 68), (96, 128), (96, 132), (128, 1000), (52, 260), (27, 2052)])
+def test_short_and_ragged_with_state(shape):
+    """T around the 64-sample chunk and the 2-chunk tracked tail; channel counts that leave
+    dead lanes; non-zero initial DF1 state in and out."""
+    rng = np.random.default_rng(sum(shape))
+    x = rng.standard_normal(shape).astype(np.float32)
+    sos = sps.cheby1(4, 1.0, 0.3, output="sos")
+    sx0 = rng.standard_normal((2, shape[0], 2))
+    sy0 = rng.standard_normal((2, shape[0], 2))
+    want, wsx, wsy = oracle.sos_cascade(x, sos, sx0, sy0)
+    y, sx, sy, xt = run(x, sos, sx0.copy(), sy0.copy(), precision="f64")
+    assert uses_tma(xt)
+    assert rel_to_max(y, want) < TOL_F64REC
+    np.testing.assert_allclose(sx, wsx, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(sy, wsy, rtol=1e-5, atol=1e-5)
+
+
+def test_time_split_many_channels_matches_generic_and_oracle():
+    rng = np.random.default_rng(7)
+    x = (0.1 * rng.standard_normal((64, 1 << 19))).astype(np.float32)
+    sos = sps.butter(8, 5000 / 24000, output="sos")
+    pick = [0, 31, 32, 63]
+    want, _, wsy = oracle.sos_cascade(x[pick], sos)
+    y_t, _, sy_t, _ = run(x, sos, precision="f32")
+    y_g, _, sy_g, _ = run(x, sos, precision="f32", no_tma=True)
+    y_n, _, _, _ = run(x, sos, precision="f32", no_split=True)
+    assert rel_to_max(y_t[pick], want) < TOL_F32
+    assert rel_to_max(y_g[pick], want) < TOL_F32
+    assert rel_to_max(y_t, y_n) < 2e-6   # split vs unsplit: warm-up truncation only
+    assert rel_to_max(y_t, y_g) < 2e-6   # the two kernels agree
+    np.testing.assert_allclose(sy_t, sy_g, rtol=1e-4, atol=1e-6 * np.abs(wsy).max())
+
+
+def test_chunked_stream_and_in_place():
+    rng = np.random.default_rng(9)
+    x = (0.1 * rng.standard_normal((64, 100000))).astype(np.float32)
+    sos_np = sps.butter(8, 5000 / 24000, output="sos")
+    sos = torch.from_numpy(sos_np)
+    want, _, wsy = oracle.sos_cascade(x, sos_np)
+    xt = torch.from_numpy(x).to(DEV)
+    sx = torch.zeros(4, 64, 2, dtype=torch.float64, device=DEV)
+    sy = torch.zeros_like(sx)
+    for lo, hi in ((0, 30000), (30000, 30004), (30004, 100000)):
+        blk = xt[:, lo:hi]
+        _ops.sos_cascade_(blk, sos, sx, sy, out=blk, force_tma=True)  # in place on a strided view
+    assert rel_to_max(xt.cpu().numpy(), want) < TOL_F32
+    np.testing.assert_allclose(sy.cpu().numpy(), wsy, rtol=1e-3, atol=1e-5 * np.abs(wsy).max())
+
+
+def test_f64_io():
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((40, 5000))
+    x = np.concatenate([x, x[:12]], 0)  # 52 channels
+    sos = sps.ellip(6, 0.5, 50, 0.25, output="sos")
+    sx0 = rng.standard_normal((3, 52, 2))
+    sy0 = rng.standard_normal((3, 52, 2))
+    want, wsx, wsy = oracle.sos_cascade(x, sos, sx0, sy0)
+    y, sx, sy, xt = run(x, sos, sx0.copy(), sy0.copy())
+    assert uses_tma(xt)
+    np.testing.assert_allclose(y, want, rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(sx, wsx, rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(sy, wsy, rtol=1e-9, atol=1e-10)
+
+
+def test_out_of_place_keeps_input():
+    rng = np.random.default_rng(33)
+    x = (0.1 * rng.standard_normal((32, 70000))).astype(np.float32)
+    sos = sps.butter(4, 0.2, output="sos")
+    want, _, _ = oracle.sos_cascade(x, sos)
+    xt = torch.from_numpy(x).to(DEV)
+    y = _ops.sos_cascade_(xt, torch.from_numpy(sos), None, None, force_tma=True)
+    assert torch.equal(xt.cpu(), torch.from_numpy(x))
+    assert rel_to_max(y.cpu().numpy(), want) < TOL_F32

@@ -19,12 +19,13 @@ from ctypes import c_char_p, c_double, c_int, c_int64, c_size_t, c_uint32, c_uin
 import torch
 
 LIB_NAME = "libtorchfx_b200.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", LIB_NAME)
+# TFX_B200_LIB: developer override used by tools/ to A/B kernel-geometry variants.
+LIB_PATH = os.environ.get("TFX_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", LIB_NAME)
 
 # flags (mirror include/torchfx_b200.h)
 TFX_OK = 0
 TFX_EINVAL, TFX_ENODEVICE, TFX_ECUDA, TFX_EWORKSPACE, TFX_ENOMEM = -1, -2, -3, -4, -5
-TFX_PREC_AUTO, TFX_PREC_F32, TFX_PREC_F64, TFX_NO_SPLIT = 0, 1, 2, 4
+TFX_PREC_AUTO, TFX_PREC_F32, TFX_PREC_F64, TFX_NO_SPLIT, TFX_NO_TMA, TFX_FORCE_TMA = 0, 1, 2, 4, 8, 16
 TFX_BANK_STACK, TFX_BANK_SUM = 0, 1
 TFX_FIR_AUTO, TFX_FIR_DIRECT, TFX_FIR_OLS = 0, 1, 2
 TFX_SOS_MAX_K = 64
@@ -41,6 +42,7 @@ _SIGNATURES = {
     "tfx_sos_cascade_f32": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int, _P, _P, c_uint32, _P, c_size_t, _P]),
     "tfx_sos_cascade_f64": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int, _P, _P, c_uint32, _P, c_size_t, _P]),
     "tfx_sos_auto_precision": (c_int, [_P, c_int, _P]),
+    "tfx_sos_cascade_uses_tma": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int]),
     "tfx_sos_cascade_cpu_f32": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int, _P, _P]),
     "tfx_sos_cascade_cpu_f64": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int, _P, _P]),
     "tfx_sos_cascade_host_f32": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int, _P, _P, c_uint32, c_int64, c_int]),

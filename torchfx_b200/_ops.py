@@ -96,6 +96,8 @@ def sos_cascade_(
     out: Tensor | None = None,
     precision: str | None = None,
     no_split: bool = False,
+    no_tma: bool = False,
+    force_tma: bool = False,
 ) -> Tensor:
     """Fused K-section cascade over ``x`` ``[C, T]``; updates ``state_x`` / ``state_y``
     (``[K, C, 2]`` float64 on ``x.device``) IN PLACE and returns ``y`` (``out`` if given;
@@ -125,7 +127,8 @@ def sos_cascade_(
     ldy = y.stride(0) if C > 1 else max(T, 1)
     suffix = "f32" if cd == torch.float32 else "f64"
     if xw.is_cuda:
-        flags = _PRECISIONS[precision or _default_precision] | (N.TFX_NO_SPLIT if no_split else 0)
+        flags = (_PRECISIONS[precision or _default_precision] | (N.TFX_NO_SPLIT if no_split else 0)
+                 | (N.TFX_NO_TMA if no_tma else 0) | (N.TFX_FORCE_TMA if force_tma else 0))
         with _device_guard(xw):
             nbytes = lib.tfx_sos_cascade_workspace_bytes(C, T, K)
             ws_ptr, ws_bytes = N.workspace(xw.device, nbytes)

@@ -17,9 +17,15 @@
 // stream's, so every request is 256 contiguous bytes.  Rows sit in shared memory with a
 // 272-byte pitch so the per-lane 128-bit row reads/writes of the compute phase are
 // bank-conflict free.  The thread filters its row IN PLACE in shared memory, then the warp
-// writes the 32 rows back with coalesced 128-bit streaming stores.  Three chunks per warp
+// writes the 32 rows back with coalesced 128-bit streaming stores.  Two chunks per warp
 // are in flight (cp.async groups); warps never synchronise with each other
-// (__syncwarp only), 8 warps / SM, one wave of 148*8*32 = 37 888 streams.
+// (__syncwarp only), 12 warps / SM.
+//
+// Work distribution.  SMs do not stream at the same speed (L2-slice distance, DRAM page
+// luck): with one equal share per warp the launch ends when the slowest SM does (13 % of
+// SM-time idle in the first ncu capture, profiles/).  Long signals are therefore cut into
+// ~8 segments per resident warp and one wave of persistent warps pulls 32-stream work
+// items from a global counter.
 //
 // Segment start state.  Segment 0 starts from the caller's DF1 state (converted to DF2T in
 // f64).  Segment j > 0 gets its state from a warm-up launch of the SAME kernel that runs
@@ -34,27 +40,32 @@
 #include <cstdint>
 
 #include "common.cuh"
+#include "sos_kernels.h"
 #include "sos_plan.h"
 #include "stream_common.cuh"
 
 namespace tfx {
 namespace {
 
-constexpr int kWarps = 4;       // warps per CTA (2 CTAs per SM)
-constexpr int kStages = 3;      // chunks in flight per warp
+#ifndef TFX_WARPS
+#define TFX_WARPS 4
+#endif
+#ifndef TFX_STAGES
+#define TFX_STAGES 2
+#endif
+constexpr int kWarps = TFX_WARPS;    // warps per CTA
+constexpr int kStages = TFX_STAGES;  // chunks in flight per warp
 constexpr int kTableBytes = 3 * 32 * 8;
 constexpr int kWarpSmem = kStages * 32 * kPitch + kTableBytes;
 constexpr int kCtaSmem = kWarps * kWarpSmem;
-constexpr int kWarpsPerSm = 8;
-
-template <typename CT, int K>
-struct SosCoef {
-    CT b0[K], b1[K], b2[K], na1[K], na2[K];
-};
-template <int K>
-struct SosCoefD {
-    double b0[K], b1[K], b2[K], a1[K], a2[K];
-};
+constexpr int kCtasPerSm = kSmemPerSm / (kCtaSmem + 1024) < 8 ? kSmemPerSm / (kCtaSmem + 1024) : 8;
+constexpr int kWarpsPerSm = kCtasPerSm * kWarps;
+static_assert(kCtasPerSm >= 1, "CTA does not fit in shared memory");
+constexpr size_t kWsHeader = 256;  // workspace header (work counter)
+#ifndef TFX_OVERSUB
+#define TFX_OVERSUB 8
+#endif
+constexpr int kOversub = TFX_OVERSUB;  // work items per resident warp when the signal is long enough
 
 struct Geom {
     const void *x;
@@ -64,47 +75,24 @@ struct Geom {
     int64_t Lseg;      // segment length
     int64_t warm;      // > 0: this launch is the warm-up pass over segments 1..S-1
     int64_t nstreams;  // streams in this launch
+    void *ws_base;     // workspace start: [0, 256) work counter, then the states
     void *ws;          // [2K][C*S] segment start states (compute type)
     int64_t ws_stride;
     double *state_x;  // [K, C, 2] DF1 state of THIS pass's sections (or NULL)
     double *state_y;
     int vec_ok;  // all rows 16-byte aligned -> 128-bit global accesses allowed
+    unsigned long long *counter;  // dynamic work distribution (NULL: one item per warp)
 };
 
-template <typename CT, int K>
-__device__ __forceinline__ CT sos_step(const SosCoef<CT, K> &cf, CT (&s1)[K], CT (&s2)[K], CT v) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const CT y = fma_rn(cf.b0[k], v, s1[k]);
-        s1[k] = fma_rn(cf.na1[k], y, fma_rn(cf.b1[k], v, s2[k]));
-        s2[k] = fma_rn(cf.na2[k], y, cf.b2[k] * v);
-        v = y;
-    }
-    return v;
-}
-
-template <typename CT, int K>
-__device__ __forceinline__ void filter_vec(const SosCoef<CT, K> &cf, CT (&s1)[K], CT (&s2)[K], float4 &a) {
-    a.x = static_cast<float>(sos_step<CT, K>(cf, s1, s2, static_cast<CT>(a.x)));
-    a.y = static_cast<float>(sos_step<CT, K>(cf, s1, s2, static_cast<CT>(a.y)));
-    a.z = static_cast<float>(sos_step<CT, K>(cf, s1, s2, static_cast<CT>(a.z)));
-    a.w = static_cast<float>(sos_step<CT, K>(cf, s1, s2, static_cast<CT>(a.w)));
-}
-template <typename CT, int K>
-__device__ __forceinline__ void filter_vec(const SosCoef<CT, K> &cf, CT (&s1)[K], CT (&s2)[K], double2 &a) {
-    a.x = static_cast<double>(sos_step<CT, K>(cf, s1, s2, static_cast<CT>(a.x)));
-    a.y = static_cast<double>(sos_step<CT, K>(cf, s1, s2, static_cast<CT>(a.y)));
-}
-
 template <typename IO, typename CT, int K>
-__global__ void __launch_bounds__(kWarps * 32, 2)
+__global__ void __launch_bounds__(kWarps * 32, kCtasPerSm)
 sos_stream_kernel(const __grid_constant__ SosCoef<CT, K> cf, const __grid_constant__ SosCoefD<K> cd,
                   const __grid_constant__ Geom g) {
     using Tr = IoTraits<IO>;
     using Vec = typename Tr::Vec;
     constexpr int CH = Tr::CHUNK;
     constexpr int VEC = Tr::VEC;
-    constexpr int NV = CH / VEC;  // 16 vectors per row
+    constexpr int NV = kNvec;  // 16-byte vectors per row
     constexpr int UV = K <= 2 ? 16 : (K <= 4 ? 8 : 4);
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -118,10 +106,22 @@ sos_stream_kernel(const __grid_constant__ SosCoef<CT, K> cf, const __grid_consta
     const IO *__restrict__ xg = static_cast<const IO *>(g.x);
     IO *__restrict__ yg = static_cast<IO *>(g.y);
 
-    // ---- which stream am I --------------------------------------------------------------
-    const int64_t q = (static_cast<int64_t>(blockIdx.x) * kWarps + warp) * 32 + lane;
-    const bool live = q < g.nstreams;
+    // ---- work items: one item = 32 consecutive streams -----------------------------------
+    // Static: item = global warp id (one item per warp).  Dynamic (g.counter != NULL): the
+    // launch is one wave of persistent warps that pull items from a global counter, so SMs
+    // that stream faster take more of the (many, short) segments and all finish together.
     const bool warm_pass = g.warm > 0;
+    const int64_t nitems = (g.nstreams + 31) / 32;
+    int64_t item = static_cast<int64_t>(blockIdx.x) * kWarps + warp;
+  for (;;) {
+    if (g.counter != nullptr) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(g.counter, 1ULL);
+        item = static_cast<int64_t>(__shfl_sync(0xffffffffu, t, 0));
+    }
+    if (item >= nitems) break;
+    const int64_t q = item * 32 + lane;
+    const bool live = q < g.nstreams;
     int64_t c = 0, j = 0, n0 = 0, n1 = 0;
     if (live) {
         if (warm_pass) {
@@ -178,18 +178,37 @@ sos_stream_kernel(const __grid_constant__ SosCoef<CT, K> cf, const __grid_consta
     const int64_t nch = (maxlen + CH - 1) / CH;
     __syncwarp();
 
-    const int piece = lane & 15;
-    const int half = lane >> 4;
+    // cooperative row copies: kNvec lanes cover one row (16 bytes each), 32/kNvec rows per instruction
+    constexpr int RPI = 32 / kNvec > 0 ? 32 / kNvec : 1;   // rows per instruction
+    constexpr int IPR = kNvec / 32 > 0 ? kNvec / 32 : 1;   // instructions per row (rows longer than 512 B)
+    const int piece = lane % kNvec;
+    const int half = lane / kNvec;
 
     auto issue_load = [&](int64_t i, int stage) {
         unsigned char *buf = wsm + stage * (32 * kPitch);
         const int64_t base = i * CH;
-        const bool all_full = __all_sync(0xffffffffu, len - base >= CH);
-        if (all_full && g.vec_ok) {
+        // A row is "full" (a whole chunk left), "empty" (its stream has ended) or partial.
+        // All full: unconditional, fully unrolled copies (the steady state).  Full or empty:
+        // the same copies under a per-row predicate.  Only a partial row -- at most one chunk
+        // per stream -- needs the element-wise path.
+        const unsigned fullmask = __ballot_sync(0xffffffffu, len - base >= CH);
+        if (fullmask == 0xffffffffu && g.vec_ok) {
 #pragma unroll
-            for (int t = 0; t < 16; ++t) {
-                const int r = 2 * t + half;
-                cp_async<16>(buf + r * kPitch + piece * 16, xg + t_offx[r] + base + piece * VEC);
+            for (int t = 0; t < 32 / RPI; ++t) {
+                const int r = RPI * t + half;
+#pragma unroll
+                for (int u = 0; u < IPR; ++u)
+                    cp_async<16>(buf + r * kPitch + (piece + 32 * u) * 16, xg + t_offx[r] + base + (piece + 32 * u) * VEC);
+            }
+        } else if ((fullmask | __ballot_sync(0xffffffffu, len - base <= 0)) == 0xffffffffu && g.vec_ok) {
+#pragma unroll 1
+            for (int t = 0; t < 32 / RPI; ++t) {
+                const int r = RPI * t + half;
+                if ((fullmask >> r) & 1u) {
+#pragma unroll
+                    for (int u = 0; u < IPR; ++u)
+                        cp_async<16>(buf + r * kPitch + (piece + 32 * u) * 16, xg + t_offx[r] + base + (piece + 32 * u) * VEC);
+                }
             }
         } else {
             for (int r = 0; r < 32; ++r) {
@@ -213,10 +232,11 @@ sos_stream_kernel(const __grid_constant__ SosCoef<CT, K> cf, const __grid_consta
         __syncwarp();
         unsigned char *buf = wsm + stage * (32 * kPitch);
         const int64_t base = i * CH;
-        const bool all_full = __all_sync(0xffffffffu, len - base >= CH);
+        const unsigned fullmask = __ballot_sync(0xffffffffu, len - base >= CH);
+        const bool clean = fullmask == 0xffffffffu || (fullmask | __ballot_sync(0xffffffffu, len - base <= 0)) == 0xffffffffu;
 
         // ---- filter my row in place -------------------------------------------------------
-        if (all_full) {
+        if (len - base >= CH) {
             Vec *row = reinterpret_cast<Vec *>(buf + lane * kPitch);
 #pragma unroll UV
             for (int v = 0; v < NV; ++v) {
@@ -234,12 +254,27 @@ sos_stream_kernel(const __grid_constant__ SosCoef<CT, K> cf, const __grid_consta
 
         // ---- write the 32 rows back, coalesced --------------------------------------------
         if (!warm_pass) {
-            if (all_full && g.vec_ok) {
+            if (fullmask == 0xffffffffu && g.vec_ok) {
 #pragma unroll
-                for (int t = 0; t < 16; ++t) {
-                    const int r = 2 * t + half;
-                    const Vec v = *reinterpret_cast<const Vec *>(buf + r * kPitch + piece * 16);
-                    st_stream16(yg + t_offy[r] + base + piece * VEC, v);
+                for (int t = 0; t < 32 / RPI; ++t) {
+                    const int r = RPI * t + half;
+#pragma unroll
+                    for (int u = 0; u < IPR; ++u) {
+                        const Vec v = *reinterpret_cast<const Vec *>(buf + r * kPitch + (piece + 32 * u) * 16);
+                        st_stream16(yg + t_offy[r] + base + (piece + 32 * u) * VEC, v);
+                    }
+                }
+            } else if (clean && g.vec_ok) {
+#pragma unroll 1
+                for (int t = 0; t < 32 / RPI; ++t) {
+                    const int r = RPI * t + half;
+                    if ((fullmask >> r) & 1u) {
+#pragma unroll
+                        for (int u = 0; u < IPR; ++u) {
+                            const Vec v = *reinterpret_cast<const Vec *>(buf + r * kPitch + (piece + 32 * u) * 16);
+                            st_stream16(yg + t_offy[r] + base + (piece + 32 * u) * VEC, v);
+                        }
+                    }
                 }
             } else {
                 for (int r = 0; r < 32; ++r) {
@@ -258,16 +293,13 @@ sos_stream_kernel(const __grid_constant__ SosCoef<CT, K> cf, const __grid_consta
     }
     cp_async_wait<0>();
 
-    if (!live) return;
-
-    if (warm_pass) {
+    if (live && warm_pass) {
         CT *wsp = static_cast<CT *>(g.ws) + (c * g.S + j);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             wsp[(2 * k) * g.ws_stride] = s1[k];
             wsp[(2 * k + 1) * g.ws_stride] = s2[k];
         }
-        return;
     }
 
     // ---- last two samples of the channel + DF1 state out ----------------------------------
@@ -308,6 +340,9 @@ sos_stream_kernel(const __grid_constant__ SosCoef<CT, K> cf, const __grid_consta
             g.state_y[o + 1] = static_cast<double>(hy[k][1]);
         }
     }
+    if (g.counter == nullptr) break;
+    __syncwarp();  // the per-warp tables are rewritten by the next item
+  }
 }
 
 template <typename IO, typename CT, int K>
@@ -343,7 +378,14 @@ int launch_k(const SosSection *sec, Geom g, const Segmentation &seg, cudaStream_
     }
     g.warm = 0;
     g.nstreams = g.C * seg.S;
-    const int64_t grid = (g.nstreams + per_cta - 1) / per_cta;
+    int64_t grid = (g.nstreams + per_cta - 1) / per_cta;
+    const int64_t resident = static_cast<int64_t>(sm_count()) * kCtasPerSm;
+    if (seg.S > 1 && grid > resident) {
+        // more items than one wave holds: persistent warps + work counter (first 8 bytes of ws)
+        g.counter = static_cast<unsigned long long *>(g.ws_base);
+        TFX_CUDA_TRY(cudaMemsetAsync(g.counter, 0, sizeof(unsigned long long), stream));
+        grid = resident;
+    }
     kern<<<static_cast<unsigned>(grid), kWarps * 32, kCtaSmem, stream>>>(cf, cd, g);
     TFX_CHECK_LAUNCH("sos_stream_kernel");
     return TFX_OK;
@@ -362,6 +404,16 @@ int launch_pass(const SosSection *sec, int k, const Geom &g, const Segmentation 
         case 8: return launch_k<IO, CT, 8>(sec, g, seg, stream);
         default: set_error("internal: pass with %d sections", k); return TFX_EINVAL;
     }
+}
+
+// Kernel choice.  Measured on B200 (profiles/): the TMA tile path is capped near 4.6 TB/s by
+// the per-SM TMA request rate on DRAM-missing 128-byte rows, the cp.async path streams
+// faster but spends more issue slots per sample; TMA wins once the recurrence is heavy
+// (float64 or >= 6 sections).
+bool want_tma(uint32_t flags, uint32_t prec, int k) {
+    if (flags & TFX_NO_TMA) return false;
+    if (flags & TFX_FORCE_TMA) return true;
+    return prec == TFX_PREC_F64 || k >= 6;
 }
 
 int64_t stream_capacity() { return static_cast<int64_t>(sm_count()) * kWarpsPerSm * 32; }
@@ -386,12 +438,39 @@ int sos_cascade_device(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, in
     TFX_REQUIRE(prec == TFX_PREC_F32 || prec == TFX_PREC_F64, "sos cascade: bad precision flag");
     const bool no_split = (flags & TFX_NO_SPLIT) != 0;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-    const int64_t capacity = stream_capacity();
 
     for (size_t pi = 0; pi < plan->passes.size(); ++pi) {
         const SosPass &p = plan->passes[pi];
         const int64_t warm_needed = prec == TFX_PREC_F32 ? p.warm_f32 : (sizeof(IO) == 4 ? p.warm_f64_io32 : p.warm_f64_io64);
-        const Segmentation seg = choose_segmentation(C, T, warm_needed, capacity, no_split);
+        const IO *px = pi == 0 ? x : y;
+        const int64_t pldx = pi == 0 ? ldx : ldy;
+        if (want_tma(flags, prec, p.k) && tma_path_ok(px, y, C, T, pldx, ldy, sizeof(IO))) {
+            // TMA-tiled kernel: a warp is 32 consecutive channels, so segments are counted per
+            // channel GROUP (capacity / 32 warps in one wave).
+            const int64_t lanes = (C + 31) / 32 * 32;
+            const Segmentation seg = choose_segmentation(lanes, T, warm_needed, tma_stream_capacity(), no_split);
+            if (seg.S > 1) {
+                const size_t need = static_cast<size_t>(2 * p.k) * static_cast<size_t>(C * seg.S) * (prec == TFX_PREC_F32 ? 4 : 8);
+                if (workspace == nullptr || workspace_bytes < need) {
+                    set_error("sos cascade: workspace of %zu bytes needed, %zu given (query tfx_sos_cascade_workspace_bytes)", need,
+                              workspace_bytes);
+                    return TFX_EWORKSPACE;
+                }
+            }
+            double *psx = state_x ? state_x + static_cast<int64_t>(p.k0) * C * 2 : nullptr;
+            double *psy = state_y ? state_y + static_cast<int64_t>(p.k0) * C * 2 : nullptr;
+            if (prec == TFX_PREC_F32) {
+                if constexpr (sizeof(IO) == 4)
+                    rc = launch_tma_pass<IO, float>(px, y, C, T, pldx, ldy, plan->sec.data() + p.k0, p.k, seg, workspace, psx, psy, stream);
+                else
+                    rc = TFX_EINVAL;
+            } else {
+                rc = launch_tma_pass<IO, double>(px, y, C, T, pldx, ldy, plan->sec.data() + p.k0, p.k, seg, workspace, psx, psy, stream);
+            }
+            if (rc != TFX_OK) return rc;
+            continue;
+        }
+        const Segmentation seg = choose_segmentation(C, T, warm_needed, stream_capacity(), no_split, kOversub);
         Geom g{};
         g.x = pi == 0 ? static_cast<const void *>(x) : static_cast<const void *>(y);
         g.y = y;
@@ -401,15 +480,17 @@ int sos_cascade_device(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, in
         g.T = T;
         g.S = seg.S;
         g.Lseg = seg.Lseg;
-        g.ws = workspace;
+        g.ws_base = workspace;
+        g.ws = workspace ? static_cast<unsigned char *>(workspace) + kWsHeader : nullptr;
         g.ws_stride = C * seg.S;
+        g.counter = nullptr;
         g.state_x = state_x ? state_x + static_cast<int64_t>(p.k0) * C * 2 : nullptr;
         g.state_y = state_y ? state_y + static_cast<int64_t>(p.k0) * C * 2 : nullptr;
         const size_t esz = sizeof(IO);
         g.vec_ok = (reinterpret_cast<uintptr_t>(g.x) % 16 == 0) && (reinterpret_cast<uintptr_t>(g.y) % 16 == 0) &&
                    ((g.ldx * esz) % 16 == 0) && ((g.ldy * esz) % 16 == 0) && (seg.S == 1 || (seg.Lseg * esz) % 16 == 0);
         if (seg.S > 1) {
-            const size_t need = static_cast<size_t>(2 * p.k) * static_cast<size_t>(C * seg.S) * (prec == TFX_PREC_F32 ? 4 : 8);
+            const size_t need = kWsHeader + static_cast<size_t>(2 * p.k) * static_cast<size_t>(C * seg.S) * (prec == TFX_PREC_F32 ? 4 : 8);
             if (workspace == nullptr || workspace_bytes < need) {
                 set_error("sos cascade: workspace of %zu bytes needed, %zu given (query tfx_sos_cascade_workspace_bytes)", need,
                           workspace_bytes);
@@ -439,9 +520,9 @@ size_t tfx_sos_cascade_workspace_bytes(int64_t C, int64_t T, int K) {
     (void)T;
     if (C <= 0 || K <= 0) return 0;
     // S > 1 only when C*S <= one wave of streams; state is 2 values per fused section.
-    const int64_t streams = std::max<int64_t>(tfx::stream_capacity(), 0) + 128;
+    const int64_t streams = std::max<int64_t>(tfx::stream_capacity() * tfx::kOversub, tfx::tma_stream_capacity()) + C + 128;
     const int kf = K < TFX_SOS_MAX_FUSED ? K : TFX_SOS_MAX_FUSED;
-    return static_cast<size_t>(2 * kf) * static_cast<size_t>(streams) * 8 + 256;
+    return tfx::kWsHeader + static_cast<size_t>(2 * kf) * static_cast<size_t>(streams) * 8 + 256;
 }
 
 int tfx_sos_cascade_f32(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
@@ -456,6 +537,11 @@ int tfx_sos_cascade_f64(const double *x, double *y, int64_t C, int64_t T, int64_
                         void *workspace, size_t workspace_bytes, void *stream) {
     return tfx::sos_cascade_device<double>(x, y, C, T, ldx, ldy, sos_host, K, state_x, state_y, flags, workspace,
                                            workspace_bytes, stream);
+}
+
+int tfx_sos_cascade_uses_tma(const void *x, const void *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, int elem_bytes) {
+    if (tfx::require_device() != TFX_OK) return 0;
+    return tfx::tma_path_ok(x, y, C, T, ldx, ldy, elem_bytes) ? 1 : 0;
 }
 
 int tfx_sos_auto_precision(const double *sos_host, int K, double *probe_rel_err) {

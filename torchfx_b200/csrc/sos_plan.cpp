@@ -236,23 +236,31 @@ std::shared_ptr<const SosPlan> get_sos_plan(const double *sos_host, int K) {
     return plan;
 }
 
-Segmentation choose_segmentation(int64_t C, int64_t T, int64_t warm_needed, int64_t capacity, bool no_split) {
+Segmentation choose_segmentation(int64_t C, int64_t T, int64_t warm_needed, int64_t capacity, bool no_split, int oversub) {
     Segmentation g;
     g.S = 1;
     g.Lseg = T;
     g.warm = 0;
     if (no_split || warm_needed < 0 || C <= 0 || T <= 0) return g;
-    const int64_t warm = (warm_needed + 3) / 4 * 4;
-    // One full wave of streams is the optimum: fewer leaves SMs idle, more only adds
-    // warm-up work.  A segment must be at least as long as its warm-up (<= 2x work) and
-    // long enough to amortise the pipeline prologue.
-    const int64_t min_seg = std::max<int64_t>(512, warm);
+    // Segment starts (and warm-up starts) are kept 64-element aligned so that every 256-byte
+    // chunk a stream moves is exactly two full 128-byte lines in both directions.
+    constexpr int64_t kAlign = 64;
+    const int64_t warm = (warm_needed + kAlign - 1) / kAlign * kAlign;
+    // One full wave of streams is the minimum worth having: fewer leaves SMs idle.  A
+    // segment must be at least as long as its warm-up (<= 2x work) and long enough to
+    // amortise the pipeline prologue.
     int64_t S = capacity / C;
     if (S < 2) return g;
-    S = std::min<int64_t>(S, T / min_seg);
+    S = std::min<int64_t>(S, T / std::max<int64_t>(512, warm));
+    if (oversub > 1) {
+        // Dynamic scheduling wants several items per resident warp; take them only while the
+        // warm-up stays <= 1/16 of a segment.
+        const int64_t fine = std::min<int64_t>(capacity / C * oversub, T / std::max<int64_t>(4096, 16 * warm));
+        S = std::max(S, fine);
+    }
     while (S >= 2) {
         int64_t L = (T + S - 1) / S;
-        L = (L + 3) / 4 * 4;
+        L = (L + kAlign - 1) / kAlign * kAlign;
         const int64_t S2 = (T + L - 1) / L;
         const int64_t last = T - (S2 - 1) * L;
         if (S2 >= 2 && last >= 2) {

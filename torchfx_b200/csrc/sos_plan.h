@@ -41,10 +41,12 @@ std::shared_ptr<const SosPlan> get_sos_plan(const double *sos_host, int K);
 // Time segmentation of one launch.
 struct Segmentation {
     int64_t S = 1;     // segments per channel
-    int64_t Lseg = 0;  // segment length in samples (multiple of 4 when S > 1)
-    int64_t warm = 0;  // warm-up samples (multiple of 4; 0 when S == 1)
+    int64_t Lseg = 0;  // segment length in samples (multiple of 64 when S > 1)
+    int64_t warm = 0;  // warm-up samples (multiple of 64; 0 when S == 1)
 };
-// `capacity` = number of streams the GPU holds in one wave (SMs * warps/SM * 32).
-Segmentation choose_segmentation(int64_t C, int64_t T, int64_t warm_needed, int64_t capacity, bool no_split);
+// `capacity` = number of streams the GPU holds in one wave (SMs * warps/SM * 32);
+// `oversub` > 1 asks for that many work items per resident warp (dynamic scheduling).
+Segmentation choose_segmentation(int64_t C, int64_t T, int64_t warm_needed, int64_t capacity, bool no_split,
+                                 int oversub = 1);
 
 }  // namespace tfx

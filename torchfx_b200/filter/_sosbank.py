@@ -46,7 +46,7 @@ class SosBank:
                 f.compute_coefficients()
             rows.append(f._sos)
         kb = max(r.shape[0] for r in rows)
-        if kb > MAX_KB or len(rows) * kb > N.TFX_BANK_MAX_LANES * 8:
+        if kb > MAX_KB:
             return None
         key = tuple(r.data_ptr() for r in rows) + tuple(int(r._version) for r in rows)
         if key != self._sos_key:
