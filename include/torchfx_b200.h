@@ -61,6 +61,9 @@ extern "C" {
 #define TFX_NO_TMA      0x8u  /* cascade kernel choice: never / always (where eligible, see        */
 #define TFX_FORCE_TMA   0x10u /* tfx_sos_cascade_uses_tma) take the TMA-tiled kernel; neither =   */
                               /* the library's heuristic (A/B timing, tests)                      */
+#define TFX_PACKED      0x20u /* float32 recurrence: opt in to the packed-pair FFMA2 kernel (two   */
+                              /* streams per thread); measured slower than the scalar kernel on   */
+                              /* B200, kept for A/B timing and tests                  */
 #define TFX_NO_SPLIT    0x4u /* never split a channel in time (one sequential stream per     */
                              /* channel; exact for unstable filters; used by tests)          */
 

@@ -129,3 +129,22 @@ def test_out_of_place_keeps_input():
     y = _ops.sos_cascade_(xt, torch.from_numpy(sos), None, None, force_tma=True)
     assert torch.equal(xt.cpu(), torch.from_numpy(x))
     assert rel_to_max(y.cpu().numpy(), want) < TOL_F32
+
+
+@pytest.mark.parametrize("K", [1, 4, 8])
+def test_packed_ffma2_kernel_matches(K):
+    """Opt-in packed-pair (FFMA2) kernel: two streams per thread."""
+    rng = np.random.default_rng(500 + K)
+    x = (0.1 * rng.standard_normal((37, 150001))).astype(np.float32)  # odd T: ragged rows; 37 ch: half-empty tiles
+    sos = sps.butter(2 * K, 0.21, output="sos")
+    sx0 = rng.standard_normal((K, 37, 2)) * 0.1
+    sy0 = rng.standard_normal((K, 37, 2)) * 0.1
+    want, wsx, wsy = oracle.sos_cascade(x, sos, sx0, sy0)
+    y, sx, sy, _ = run(x, sos, sx0.copy(), sy0.copy(), precision="f32", packed=True, no_tma=True)
+    assert rel_to_max(y, want) < TOL_F32
+    np.testing.assert_allclose(sx, wsx, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(sy, wsy, rtol=1e-3, atol=1e-4 * max(np.abs(wsy).max(), 1e-30))
+    xa = (0.1 * rng.standard_normal((64, 1 << 18))).astype(np.float32)
+    wa, _, _ = oracle.sos_cascade(xa[:4], sos)
+    ya, _, _, _ = run(xa, sos, precision="f32", packed=True, no_tma=True)
+    assert rel_to_max(ya[:4], wa) < TOL_F32

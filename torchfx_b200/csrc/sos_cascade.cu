@@ -61,28 +61,6 @@ constexpr int kCtaSmem = kWarps * kWarpSmem;
 constexpr int kCtasPerSm = kSmemPerSm / (kCtaSmem + 1024) < 8 ? kSmemPerSm / (kCtaSmem + 1024) : 8;
 constexpr int kWarpsPerSm = kCtasPerSm * kWarps;
 static_assert(kCtasPerSm >= 1, "CTA does not fit in shared memory");
-constexpr size_t kWsHeader = 256;  // workspace header (work counter)
-#ifndef TFX_OVERSUB
-#define TFX_OVERSUB 8
-#endif
-constexpr int kOversub = TFX_OVERSUB;  // work items per resident warp when the signal is long enough
-
-struct Geom {
-    const void *x;
-    void *y;
-    int64_t ldx, ldy, C, T;
-    int64_t S;         // segments per channel
-    int64_t Lseg;      // segment length
-    int64_t warm;      // > 0: this launch is the warm-up pass over segments 1..S-1
-    int64_t nstreams;  // streams in this launch
-    void *ws_base;     // workspace start: [0, 256) work counter, then the states
-    void *ws;          // [2K][C*S] segment start states (compute type)
-    int64_t ws_stride;
-    double *state_x;  // [K, C, 2] DF1 state of THIS pass's sections (or NULL)
-    double *state_y;
-    int vec_ok;  // all rows 16-byte aligned -> 128-bit global accesses allowed
-    unsigned long long *counter;  // dynamic work distribution (NULL: one item per warp)
-};
 
 template <typename IO, typename CT, int K>
 __global__ void __launch_bounds__(kWarps * 32, kCtasPerSm)
@@ -470,7 +448,10 @@ int sos_cascade_device(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, in
             if (rc != TFX_OK) return rc;
             continue;
         }
-        const Segmentation seg = choose_segmentation(C, T, warm_needed, stream_capacity(), no_split, kOversub);
+        // opt-in: float32 recurrence on the packed FP32 pipe (FFMA2), two streams per thread
+        const bool packed = sizeof(IO) == 4 && prec == TFX_PREC_F32 && (flags & TFX_PACKED);
+        const Segmentation seg =
+            choose_segmentation(C, T, warm_needed, packed ? packed_stream_capacity() : stream_capacity(), no_split, kOversub);
         Geom g{};
         g.x = pi == 0 ? static_cast<const void *>(x) : static_cast<const void *>(y);
         g.y = y;
@@ -497,7 +478,9 @@ int sos_cascade_device(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, in
                 return TFX_EWORKSPACE;
             }
         }
-        if (prec == TFX_PREC_F32) {
+        if (packed) {
+            rc = launch_packed_pass(plan->sec.data() + p.k0, p.k, g, seg, stream);
+        } else if (prec == TFX_PREC_F32) {
             if constexpr (sizeof(IO) == 4) {
                 rc = launch_pass<IO, float>(plan->sec.data() + p.k0, p.k, g, seg, stream);
             } else {
@@ -520,7 +503,8 @@ size_t tfx_sos_cascade_workspace_bytes(int64_t C, int64_t T, int K) {
     (void)T;
     if (C <= 0 || K <= 0) return 0;
     // S > 1 only when C*S <= one wave of streams; state is 2 values per fused section.
-    const int64_t streams = std::max<int64_t>(tfx::stream_capacity() * tfx::kOversub, tfx::tma_stream_capacity()) + C + 128;
+    const int64_t streams = std::max<int64_t>(std::max(tfx::stream_capacity(), tfx::packed_stream_capacity()) * tfx::kOversub,
+                                              tfx::tma_stream_capacity()) + C + 128;
     const int kf = K < TFX_SOS_MAX_FUSED ? K : TFX_SOS_MAX_FUSED;
     return tfx::kWsHeader + static_cast<size_t>(2 * kf) * static_cast<size_t>(streams) * 8 + 256;
 }

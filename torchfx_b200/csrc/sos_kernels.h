@@ -9,6 +9,35 @@
 
 namespace tfx {
 
+constexpr size_t kWsHeader = 256;  // workspace header (work counter)
+#ifndef TFX_OVERSUB
+#define TFX_OVERSUB 8
+#endif
+constexpr int kOversub = TFX_OVERSUB;  // work items per resident warp when the signal is long enough
+
+// Launch geometry shared by the cp.async stream kernels (sos_cascade.cu, sos_packed.cu).
+struct Geom {
+    const void *x;
+    void *y;
+    int64_t ldx, ldy, C, T;
+    int64_t S;         // segments per channel
+    int64_t Lseg;      // segment length
+    int64_t warm;      // > 0: this launch is the warm-up pass over segments 1..S-1
+    int64_t nstreams;  // streams in this launch
+    void *ws_base;     // workspace start: [0, 256) work counter, then the states
+    void *ws;          // [2K][C*S] segment start states (compute type)
+    int64_t ws_stride;
+    double *state_x;  // [K, C, 2] DF1 state of THIS pass's sections (or NULL)
+    double *state_y;
+    int vec_ok;  // all rows 16-byte aligned -> 128-bit global accesses allowed
+    unsigned long long *counter;  // dynamic work distribution (NULL: one item per warp)
+};
+
+
+// Packed-pair kernel (sos_packed.cu): float32 only, two streams per thread on FFMA2.
+int64_t packed_stream_capacity();
+int launch_packed_pass(const SosSection *sec, int k, Geom g, const Segmentation &seg, cudaStream_t stream);
+
 // TMA-tiled kernel (sos_tma.cu): lanes = 32 consecutive channels.
 bool tma_path_ok(const void *x, const void *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, int elem_bytes);
 int64_t tma_stream_capacity();  // streams (lanes) resident in one wave
