@@ -356,7 +356,7 @@ def main() -> None:
         "unit": "GB/s",
         "frac": achieved / peak,
         "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
-        "kernel": "sos_stream_kernel<float,float,4> (cp.async tiles, persistent warps)",
+        "kernel": "sos_tile_kernel<float,float,4> (32-channel x 64-sample cp.async tiles, persistent warps)",
         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SAMPLE * C * T,
         "peak_source": peak_src,
         "per_gpu": True,

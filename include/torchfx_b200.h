@@ -64,6 +64,8 @@ extern "C" {
 #define TFX_PACKED      0x20u /* float32 recurrence: opt in to the packed-pair FFMA2 kernel (two   */
                               /* streams per thread); measured slower than the scalar kernel on   */
                               /* B200, kept for A/B timing and tests                  */
+#define TFX_NO_TILE     0x40u /* never take the channel-tile kernel (lanes = channels); use the    */
+                              /* stream-per-lane kernel even for many channels (A/B, tests)       */
 #define TFX_NO_SPLIT    0x4u /* never split a channel in time (one sequential stream per     */
                              /* channel; exact for unstable filters; used by tests)          */
 

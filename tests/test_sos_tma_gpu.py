@@ -80,7 +80,10 @@ def test_time_split_many_channels_matches_generic_and_oracle():
     pick = [0, 31, 32, 63]
     want, _, wsy = oracle.sos_cascade(x[pick], sos)
     y_t, _, sy_t, _ = run(x, sos, precision="f32")
-    y_g, _, sy_g, _ = run(x, sos, precision="f32", no_tma=True)
+    y_g, _, sy_g, _ = run(x, sos, precision="f32", no_tma=True, no_tile=True)  # stream-per-lane kernel
+    y_c, _, sy_c, _ = run(x, sos, precision="f32", no_tma=True)                # channel-tile kernel
+    assert rel_to_max(y_c[pick], want) < TOL_F32 and rel_to_max(y_c, y_g) < 2e-6
+    np.testing.assert_allclose(sy_c, sy_g, rtol=1e-4, atol=1e-6 * np.abs(wsy).max())
     y_n, _, _, _ = run(x, sos, precision="f32", no_split=True)
     assert rel_to_max(y_t[pick], want) < TOL_F32
     assert rel_to_max(y_g[pick], want) < TOL_F32

@@ -9,7 +9,7 @@ for spec in "$@"; do
   name=${spec%%:*}; flags=${spec#*:}
   (
   d=$OUT/obj_$name; mkdir -p $d
-  for f in runtime sos_cascade sos_packed sos_tma filterbank fir delay host_stream; do $NV $flags -c $ROOT/torchfx_b200/csrc/$f.cu -o $d/$f.o & done
+  for f in runtime sos_cascade sos_tile sos_packed sos_tma filterbank fir delay host_stream; do $NV $flags -c $ROOT/torchfx_b200/csrc/$f.cu -o $d/$f.o & done
   for f in sos_plan cpu_twin; do $NV $flags -x cu -c $ROOT/torchfx_b200/csrc/$f.cpp -o $d/$f.o & done
   wait
   $NV -shared -o $OUT/lib_$name.so $d/*.o -Xcompiler -fopenmp -lgomp -cudart static

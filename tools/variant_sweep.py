@@ -15,10 +15,10 @@ def t(fn, reps=5):
     return e0.elapsed_time(e1) / reps
 out = {}
 for case in os.environ["VS_CASES"].split(";"):
-    parts = case.split(","); C, T, K, prec = int(parts[0]), int(parts[1]), int(parts[2]), parts[3]; tma = len(parts) > 4 and parts[4] == "tma"; pk = len(parts) > 4 and parts[4] == "pk"
+    parts = case.split(","); C, T, K, prec = int(parts[0]), int(parts[1]), int(parts[2]), parts[3]; tma = len(parts) > 4 and parts[4] == "tma"; pk = len(parts) > 4 and parts[4] == "pk"; nt = len(parts) > 4 and parts[4] == "notile"
     x = torch.empty((C, T), dtype=torch.float32, device="cuda").normal_(0, 0.1)
     sos = torch.from_numpy(sps.butter(2 * K, 5000 / 24000, output="sos")).contiguous()
-    ms = t(lambda: _ops.sos_cascade_(x, sos, None, None, out=x, precision=prec, force_tma=tma, packed=pk))
+    ms = t(lambda: _ops.sos_cascade_(x, sos, None, None, out=x, precision=prec, force_tma=tma, packed=pk, no_tile=nt))
     out[case] = round(8 * C * T / ms / 1e6, 1)
     del x
 print(json.dumps(out))

@@ -99,6 +99,7 @@ def sos_cascade_(
     no_tma: bool = False,
     force_tma: bool = False,
     packed: bool = False,
+    no_tile: bool = False,
 ) -> Tensor:
     """Fused K-section cascade over ``x`` ``[C, T]``; updates ``state_x`` / ``state_y``
     (``[K, C, 2]`` float64 on ``x.device``) IN PLACE and returns ``y`` (``out`` if given;
@@ -129,7 +130,7 @@ def sos_cascade_(
     suffix = "f32" if cd == torch.float32 else "f64"
     if xw.is_cuda:
         flags = (_PRECISIONS[precision or _default_precision] | (N.TFX_NO_SPLIT if no_split else 0)
-                 | (N.TFX_NO_TMA if no_tma else 0) | (N.TFX_FORCE_TMA if force_tma else 0) | (N.TFX_PACKED if packed else 0))
+                 | (N.TFX_NO_TMA if no_tma else 0) | (N.TFX_FORCE_TMA if force_tma else 0) | (N.TFX_PACKED if packed else 0) | (N.TFX_NO_TILE if no_tile else 0))
         with _device_guard(xw):
             nbytes = lib.tfx_sos_cascade_workspace_bytes(C, T, K)
             ws_ptr, ws_bytes = N.workspace(xw.device, nbytes)

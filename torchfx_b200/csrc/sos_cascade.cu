@@ -448,6 +448,31 @@ int sos_cascade_device(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, in
             if (rc != TFX_OK) return rc;
             continue;
         }
+        if (!(flags & TFX_NO_TILE) && !(flags & TFX_PACKED) && tile_path_ok(C)) {
+            // channel-tile kernel: a warp is 32 consecutive channels x one time segment
+            const int64_t lanes = (C + 31) / 32 * 32;
+            const Segmentation seg = choose_segmentation(lanes, T, warm_needed, tile_stream_capacity(), no_split, kOversub);
+            if (seg.S > 1) {
+                const size_t need = kWsHeader + static_cast<size_t>(2 * p.k) * static_cast<size_t>(C * seg.S) * (prec == TFX_PREC_F32 ? 4 : 8);
+                if (workspace == nullptr || workspace_bytes < need) {
+                    set_error("sos cascade: workspace of %zu bytes needed, %zu given (query tfx_sos_cascade_workspace_bytes)", need,
+                              workspace_bytes);
+                    return TFX_EWORKSPACE;
+                }
+            }
+            double *psx = state_x ? state_x + static_cast<int64_t>(p.k0) * C * 2 : nullptr;
+            double *psy = state_y ? state_y + static_cast<int64_t>(p.k0) * C * 2 : nullptr;
+            if (prec == TFX_PREC_F32) {
+                if constexpr (sizeof(IO) == 4)
+                    rc = launch_tile_pass<IO, float>(px, y, C, T, pldx, ldy, plan->sec.data() + p.k0, p.k, seg, workspace, psx, psy, stream);
+                else
+                    rc = TFX_EINVAL;
+            } else {
+                rc = launch_tile_pass<IO, double>(px, y, C, T, pldx, ldy, plan->sec.data() + p.k0, p.k, seg, workspace, psx, psy, stream);
+            }
+            if (rc != TFX_OK) return rc;
+            continue;
+        }
         // opt-in: float32 recurrence on the packed FP32 pipe (FFMA2), two streams per thread
         const bool packed = sizeof(IO) == 4 && prec == TFX_PREC_F32 && (flags & TFX_PACKED);
         const Segmentation seg =
@@ -503,7 +528,7 @@ size_t tfx_sos_cascade_workspace_bytes(int64_t C, int64_t T, int K) {
     (void)T;
     if (C <= 0 || K <= 0) return 0;
     // S > 1 only when C*S <= one wave of streams; state is 2 values per fused section.
-    const int64_t streams = std::max<int64_t>(std::max(tfx::stream_capacity(), tfx::packed_stream_capacity()) * tfx::kOversub,
+    const int64_t streams = std::max<int64_t>(std::max(std::max(tfx::stream_capacity(), tfx::packed_stream_capacity()), tfx::tile_stream_capacity()) * tfx::kOversub,
                                               tfx::tma_stream_capacity()) + C + 128;
     const int kf = K < TFX_SOS_MAX_FUSED ? K : TFX_SOS_MAX_FUSED;
     return tfx::kWsHeader + static_cast<size_t>(2 * kf) * static_cast<size_t>(streams) * 8 + 256;

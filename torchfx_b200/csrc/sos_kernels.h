@@ -38,6 +38,13 @@ struct Geom {
 int64_t packed_stream_capacity();
 int launch_packed_pass(const SosSection *sec, int k, Geom g, const Segmentation &seg, cudaStream_t stream);
 
+// Channel-tile kernel (sos_tile.cu): lanes = 32 consecutive channels, cp.async tiles.
+bool tile_path_ok(int64_t C);
+int64_t tile_stream_capacity();
+template <typename IO, typename CT>
+int launch_tile_pass(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, const SosSection *sec, int k,
+                     const Segmentation &seg, void *ws_base, double *state_x, double *state_y, cudaStream_t stream);
+
 // TMA-tiled kernel (sos_tma.cu): lanes = 32 consecutive channels.
 bool tma_path_ok(const void *x, const void *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, int elem_bytes);
 int64_t tma_stream_capacity();  // streams (lanes) resident in one wave

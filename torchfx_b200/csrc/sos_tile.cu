@@ -1,0 +1,398 @@
+// sos_tile.cu -- channel-tile variant of the fused SOS cascade: the main path when there are
+// enough channels to fill the lanes (every BASELINE config).
+//
+// A warp owns 32 CONSECUTIVE CHANNELS over one time segment; its working set is a dense
+// [32 channels x 64 samples] tile.  Compared with the stream-per-lane kernel
+// (sos_cascade.cu, still used for few channels) all 32 lanes share the segment bounds, so
+// every branch and loop count is warp-uniform, the row addresses are `base + r*ld` (no
+// per-row offset tables, no ballots), and ragged edges exist only in the very last chunk of
+// a channel.  Data path:
+//   HBM --cp.async.cg 16 B (LDGSTS, 256 contiguous bytes per half-warp)--> shared memory,
+//   stored with a 128-byte XOR swizzle (16-byte column v of row r lives at column v^(r&7))
+//   so lane r reading "its" row with 128-bit LDS/STS is bank-conflict free without padding;
+//   filtered in place; written back with coalesced 128-bit streaming stores.
+// The same tile layout is what sos_tma.cu moves with cp.async.bulk.tensor; on B200 the TMA
+// variant is capped near 4.6 TB/s by the per-SM TMA request rate on DRAM-missing 128-byte
+// rows (profiles/), the LDGSTS variant is not, so this one is the default.
+//
+// Work distribution: persistent warps pull (channel group, segment) items from a global
+// counter; segment start states come from a warm-up launch (see sos_plan.cpp).
+#include <algorithm>
+#include <cstdint>
+
+#include "common.cuh"
+#include "sos_kernels.h"
+#include "stream_common.cuh"
+
+namespace tfx {
+namespace {
+
+#ifndef TFX_T_STAGES
+#define TFX_T_STAGES 2
+#endif
+#ifndef TFX_T_WARPS
+#define TFX_T_WARPS 1
+#endif
+constexpr int kStages = TFX_T_STAGES;
+constexpr int kWarps = TFX_T_WARPS;
+constexpr int kTileBytes = 32 * 256;
+constexpr int kWarpSmem = kStages * kTileBytes;
+constexpr int kCtaSmem = kWarps * kWarpSmem + 128;  // + slack to align the tiles to 128 B
+constexpr int kCtasPerSm = std::min(32, kSmemPerSm / (kCtaSmem + 1024));
+constexpr int kWarpsPerSm = kCtasPerSm * kWarps;
+static_assert(kCtasPerSm >= 1, "CTA does not fit in shared memory");
+
+struct TileGeom {
+    const void *x;
+    void *y;
+    int64_t ldx, ldy, C, T;
+    int64_t S, Lseg, warm;
+    int64_t nitems;  // G * S (main) or G * (S - 1) (warm-up)
+    int64_t G;       // channel groups of 32
+    void *ws;        // [2K][C * S]
+    int64_t ws_stride;
+    double *state_x;
+    double *state_y;
+    unsigned long long *counter;  // NULL: item = global warp id
+    int vec_ok;
+};
+
+// byte offset of the 16-byte column v (0..15) of row r inside a swizzled tile
+__device__ __forceinline__ int col_offset(int r, int v) { return (v >> 3) * 4096 + r * 128 + (((v & 7) ^ (r & 7)) << 4); }
+template <typename IO>
+__device__ __forceinline__ int elem_offset(int r, int e) {
+    constexpr int EPV = 16 / sizeof(IO);
+    return col_offset(r, e / EPV) + (e % EPV) * static_cast<int>(sizeof(IO));
+}
+
+template <typename IO, typename CT, int K>
+__global__ void __launch_bounds__(kWarps * 32, kCtasPerSm)
+sos_tile_kernel(const __grid_constant__ SosCoef<CT, K> cf, const __grid_constant__ SosCoefD<K> cd,
+                const __grid_constant__ TileGeom g) {
+    using Tr = IoTraits<IO>;
+    using Vec = typename Tr::Vec;
+    constexpr int VEC = Tr::VEC;
+    constexpr int CH = 256 / sizeof(IO);  // samples per chunk
+    constexpr int UV = K <= 2 ? 16 : (K <= 4 ? 8 : 4);
+
+    extern __shared__ unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    unsigned char *ring = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127)) +
+                          warp * kWarpSmem;
+    const IO *__restrict__ xg = static_cast<const IO *>(g.x);
+    IO *__restrict__ yg = static_cast<IO *>(g.y);
+    const bool warm_pass = g.warm > 0;
+    const int piece = lane & 15;
+    const int half = lane >> 4;
+
+    int64_t item = static_cast<int64_t>(blockIdx.x) * kWarps + warp;
+    for (;;) {
+        if (g.counter != nullptr) {
+            unsigned long long t = 0;
+            if (lane == 0) t = atomicAdd(g.counter, 1ULL);
+            item = static_cast<int64_t>(__shfl_sync(0xffffffffu, t, 0));
+        }
+        if (item >= g.nitems) break;
+
+        // ---- the item: channel group x time segment (all warp-uniform) -----------------------
+        int64_t grp, j, n0, n1;
+        if (warm_pass) {
+            const int64_t sm1 = g.S - 1;
+            grp = item / sm1;
+            j = item - grp * sm1 + 1;
+            n1 = j * g.Lseg;
+            n0 = max(n1 - g.warm, static_cast<int64_t>(0));
+        } else {
+            grp = item / g.S;
+            j = item - grp * g.S;
+            n0 = j * g.Lseg;
+            n1 = min(g.T, n0 + g.Lseg);
+        }
+        const int64_t c0 = grp * 32;
+        const int nrows = static_cast<int>(min(static_cast<int64_t>(32), g.C - c0));
+        const int64_t c = c0 + lane;
+        const bool live = lane < nrows;
+        const bool from_true_state = n0 == 0;
+        const bool do_tail = !warm_pass && (j == g.S - 1) && g.state_x != nullptr;
+        const int64_t len = n1 - n0;
+        const int64_t nch = (len + CH - 1) / CH;
+
+        // ---- start state (DF2T) ----------------------------------------------------------------
+        CT s1[K], s2[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            s1[k] = CT(0);
+            s2[k] = CT(0);
+        }
+        if (live) {
+            if (from_true_state) {
+                if (g.state_x != nullptr) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const int64_t o = (static_cast<int64_t>(k) * g.C + c) * 2;
+                        const double x1 = g.state_x[o], x2 = g.state_x[o + 1];
+                        const double y1 = g.state_y[o], y2 = g.state_y[o + 1];
+                        s1[k] = static_cast<CT>(cd.b1[k] * x1 + cd.b2[k] * x2 - cd.a1[k] * y1 - cd.a2[k] * y2);
+                        s2[k] = static_cast<CT>(cd.b2[k] * x1 - cd.a2[k] * y1);
+                    }
+                }
+            } else if (!warm_pass) {
+                const CT *wsp = static_cast<const CT *>(g.ws) + (c * g.S + j);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    s1[k] = wsp[(2 * k) * g.ws_stride];
+                    s2[k] = wsp[(2 * k + 1) * g.ws_stride];
+                }
+            }
+        }
+
+        // row (2t + half), 16-byte piece `piece`: this lane's share of every cooperative copy
+        const IO *xrow = xg + (c0 + half) * g.ldx + n0 + piece * VEC;
+        IO *yrow = yg + (c0 + half) * g.ldy + n0 + piece * VEC;
+        const int64_t ldx2 = 2 * g.ldx, ldy2 = 2 * g.ldy;
+
+        auto issue_load = [&](int64_t i, int stage) {
+            unsigned char *tile = ring + stage * kTileBytes;
+            const int64_t base = i * CH;
+            const int cnt = static_cast<int>(min(len - base, static_cast<int64_t>(CH)));
+            if (cnt == CH && g.vec_ok) {
+                if (nrows == 32) {
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) cp_async<16>(tile + col_offset(2 * t + half, piece), xrow + t * ldx2 + base);
+                } else {
+#pragma unroll 1
+                    for (int t = 0; t < 16; ++t)
+                        if (2 * t + half < nrows) cp_async<16>(tile + col_offset(2 * t + half, piece), xrow + t * ldx2 + base);
+                }
+            } else {
+#pragma unroll 1
+                for (int r = 0; r < nrows; ++r) {
+                    const IO *src = xg + (c0 + r) * g.ldx + n0 + base;
+                    for (int e = lane; e < cnt; e += 32) cp_async<sizeof(IO)>(tile + elem_offset<IO>(r, e), src + e);
+                }
+            }
+        };
+
+#pragma unroll
+        for (int st = 0; st < kStages; ++st) {
+            if (st < nch) issue_load(st, st);
+            cp_async_commit();
+        }
+
+        // DF1 history of every section, only maintained over the channel's last two chunks
+        CT hx[K][2], hy[K][2];
+        if (do_tail) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                hx[k][0] = hx[k][1] = hy[k][0] = hy[k][1] = CT(0);
+                if (live && from_true_state) {  // consulted only when fewer than two samples are filtered (then S == 1)
+                    const int64_t o = (static_cast<int64_t>(k) * g.C + c) * 2;
+                    hx[k][0] = static_cast<CT>(g.state_x[o]);
+                    hx[k][1] = static_cast<CT>(g.state_x[o + 1]);
+                    hy[k][0] = static_cast<CT>(g.state_y[o]);
+                    hy[k][1] = static_cast<CT>(g.state_y[o + 1]);
+                }
+            }
+        }
+
+        int stage = 0;
+        for (int64_t i = 0; i < nch; ++i) {
+            cp_async_wait<kStages - 1>();
+            __syncwarp();
+            unsigned char *tile = ring + stage * kTileBytes;
+            const int64_t base = i * CH;
+            const int cnt = static_cast<int>(min(len - base, static_cast<int64_t>(CH)));
+            const bool tracked = do_tail && i >= nch - 2;
+
+            // ---- filter my row (channel) in place ----------------------------------------------
+            if (live) {
+                if (cnt == CH && !tracked) {
+#pragma unroll UV
+                    for (int v = 0; v < 16; ++v) {
+                        Vec *p = reinterpret_cast<Vec *>(tile + col_offset(lane, v));
+                        Vec a = *p;
+                        filter_vec<CT, K>(cf, s1, s2, a);
+                        *p = a;
+                    }
+                } else if (!tracked) {
+                    for (int e = 0; e < cnt; ++e) {
+                        IO *p = reinterpret_cast<IO *>(tile + elem_offset<IO>(lane, e));
+                        *p = static_cast<IO>(sos_step<CT, K>(cf, s1, s2, static_cast<CT>(*p)));
+                    }
+                } else {
+                    for (int e = 0; e < cnt; ++e) {
+                        IO *p = reinterpret_cast<IO *>(tile + elem_offset<IO>(lane, e));
+                        CT v = static_cast<CT>(*p);
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            const CT y = fma_rn(cf.b0[k], v, s1[k]);
+                            s1[k] = fma_rn(cf.na1[k], y, fma_rn(cf.b1[k], v, s2[k]));
+                            s2[k] = fma_rn(cf.na2[k], y, cf.b2[k] * v);
+                            hx[k][1] = hx[k][0];
+                            hx[k][0] = v;
+                            hy[k][1] = hy[k][0];
+                            hy[k][0] = y;
+                            v = y;
+                        }
+                        *p = static_cast<IO>(v);
+                    }
+                }
+            }
+            __syncwarp();
+
+            // ---- write the tile back, coalesced ------------------------------------------------
+            if (!warm_pass) {
+                if (cnt == CH && g.vec_ok) {
+                    if (nrows == 32) {
+#pragma unroll
+                        for (int t = 0; t < 16; ++t)
+                            st_stream16(yrow + t * ldy2 + base, *reinterpret_cast<const Vec *>(tile + col_offset(2 * t + half, piece)));
+                    } else {
+#pragma unroll 1
+                        for (int t = 0; t < 16; ++t)
+                            if (2 * t + half < nrows)
+                                st_stream16(yrow + t * ldy2 + base, *reinterpret_cast<const Vec *>(tile + col_offset(2 * t + half, piece)));
+                    }
+                } else {
+#pragma unroll 1
+                    for (int r = 0; r < nrows; ++r) {
+                        IO *dst = yg + (c0 + r) * g.ldy + n0 + base;
+                        for (int e = lane; e < cnt; e += 32) dst[e] = *reinterpret_cast<const IO *>(tile + elem_offset<IO>(r, e));
+                    }
+                }
+            }
+            __syncwarp();
+
+            if (i + kStages < nch) issue_load(i + kStages, stage);
+            cp_async_commit();
+            stage = (stage + 1 == kStages) ? 0 : stage + 1;
+        }
+        cp_async_wait<0>();
+
+        if (live) {
+            if (warm_pass) {
+                CT *wsp = static_cast<CT *>(g.ws) + (c * g.S + j);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    wsp[(2 * k) * g.ws_stride] = s1[k];
+                    wsp[(2 * k + 1) * g.ws_stride] = s2[k];
+                }
+            } else if (do_tail) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int64_t o = (static_cast<int64_t>(k) * g.C + c) * 2;
+                    g.state_x[o] = static_cast<double>(hx[k][0]);
+                    g.state_x[o + 1] = static_cast<double>(hx[k][1]);
+                    g.state_y[o] = static_cast<double>(hy[k][0]);
+                    g.state_y[o + 1] = static_cast<double>(hy[k][1]);
+                }
+            }
+        }
+        if (g.counter == nullptr) break;
+        __syncwarp();
+    }
+}
+
+template <typename IO, typename CT, int K>
+int launch_tile_k(const SosSection *sec, TileGeom g, const Segmentation &seg, unsigned long long *counter, cudaStream_t stream) {
+    SosCoef<CT, K> cf;
+    SosCoefD<K> cd;
+    for (int k = 0; k < K; ++k) {
+        cf.b0[k] = static_cast<CT>(sec[k].b0);
+        cf.b1[k] = static_cast<CT>(sec[k].b1);
+        cf.b2[k] = static_cast<CT>(sec[k].b2);
+        cf.na1[k] = static_cast<CT>(-sec[k].a1);
+        cf.na2[k] = static_cast<CT>(-sec[k].a2);
+        cd.b0[k] = sec[k].b0;
+        cd.b1[k] = sec[k].b1;
+        cd.b2[k] = sec[k].b2;
+        cd.a1[k] = sec[k].a1;
+        cd.a2[k] = sec[k].a2;
+    }
+    auto kern = sos_tile_kernel<IO, CT, K>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TFX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtaSmem));
+        attr_set = true;
+    }
+    if (seg.S > 1) {
+        TileGeom gw = g;
+        gw.warm = seg.warm;
+        gw.nitems = g.G * (seg.S - 1);
+        gw.counter = nullptr;
+        const int64_t grid = (gw.nitems + kWarps - 1) / kWarps;
+        kern<<<static_cast<unsigned>(grid), kWarps * 32, kCtaSmem, stream>>>(cf, cd, gw);
+        TFX_CHECK_LAUNCH("sos_tile_kernel(warm-up)");
+    }
+    g.warm = 0;
+    g.nitems = g.G * seg.S;
+    g.counter = nullptr;
+    int64_t grid = (g.nitems + kWarps - 1) / kWarps;
+    const int64_t resident = static_cast<int64_t>(sm_count()) * kCtasPerSm;
+    if (seg.S > 1 && grid > resident && counter != nullptr) {
+        g.counter = counter;
+        TFX_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+        grid = resident;
+    }
+    kern<<<static_cast<unsigned>(grid), kWarps * 32, kCtaSmem, stream>>>(cf, cd, g);
+    TFX_CHECK_LAUNCH("sos_tile_kernel");
+    return TFX_OK;
+}
+
+template <typename IO, typename CT>
+int launch_tile_any(const SosSection *sec, int k, const TileGeom &g, const Segmentation &seg, unsigned long long *counter,
+                    cudaStream_t stream) {
+    switch (k) {
+        case 1: return launch_tile_k<IO, CT, 1>(sec, g, seg, counter, stream);
+        case 2: return launch_tile_k<IO, CT, 2>(sec, g, seg, counter, stream);
+        case 3: return launch_tile_k<IO, CT, 3>(sec, g, seg, counter, stream);
+        case 4: return launch_tile_k<IO, CT, 4>(sec, g, seg, counter, stream);
+        case 5: return launch_tile_k<IO, CT, 5>(sec, g, seg, counter, stream);
+        case 6: return launch_tile_k<IO, CT, 6>(sec, g, seg, counter, stream);
+        case 7: return launch_tile_k<IO, CT, 7>(sec, g, seg, counter, stream);
+        case 8: return launch_tile_k<IO, CT, 8>(sec, g, seg, counter, stream);
+        default: set_error("internal: pass with %d sections", k); return TFX_EINVAL;
+    }
+}
+
+}  // namespace
+
+int64_t tile_stream_capacity() { return static_cast<int64_t>(sm_count()) * kWarpsPerSm * 32; }
+
+bool tile_path_ok(int64_t C) {
+    const int64_t G = (C + 31) / 32;
+    return C * 5 >= G * 32 * 4;  // >= 80 % of the lanes carry a channel
+}
+
+template <typename IO, typename CT>
+int launch_tile_pass(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, const SosSection *sec, int k,
+                     const Segmentation &seg, void *ws_base, double *state_x, double *state_y, cudaStream_t stream) {
+    TileGeom g{};
+    g.x = x;
+    g.y = y;
+    g.ldx = ldx;
+    g.ldy = ldy;
+    g.C = C;
+    g.T = T;
+    g.S = seg.S;
+    g.Lseg = seg.Lseg;
+    g.G = (C + 31) / 32;
+    g.ws = ws_base ? static_cast<unsigned char *>(ws_base) + kWsHeader : nullptr;
+    g.ws_stride = C * seg.S;
+    g.state_x = state_x;
+    g.state_y = state_y;
+    const size_t esz = sizeof(IO);
+    g.vec_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0) && ((ldx * esz) % 16 == 0) &&
+               ((ldy * esz) % 16 == 0);
+    return launch_tile_any<IO, CT>(sec, k, g, seg, static_cast<unsigned long long *>(ws_base), stream);
+}
+
+template int launch_tile_pass<float, float>(const float *, float *, int64_t, int64_t, int64_t, int64_t, const SosSection *, int,
+                                            const Segmentation &, void *, double *, double *, cudaStream_t);
+template int launch_tile_pass<float, double>(const float *, float *, int64_t, int64_t, int64_t, int64_t, const SosSection *, int,
+                                             const Segmentation &, void *, double *, double *, cudaStream_t);
+template int launch_tile_pass<double, double>(const double *, double *, int64_t, int64_t, int64_t, int64_t, const SosSection *,
+                                              int, const Segmentation &, void *, double *, double *, cudaStream_t);
+
+}  // namespace tfx
