@@ -349,13 +349,17 @@ def main() -> None:
     peak, peak_src = measured_hbm_peak()
     achieved = ALGO_BYTES_PER_SAMPLE * C * T / (ms_per_step * 1e-3) / 1e9
     traffic = recorded_traffic()
+    traffic_bytes = None
+    if traffic and traffic.get("traffic_over_algorithmic"):
+        traffic_bytes = traffic["traffic_over_algorithmic"] * ALGO_BYTES_PER_SAMPLE * C * T
     roofline = {
         "bound": "hbm",
         "achieved": achieved,
         "peak": peak,
         "unit": "GB/s",
         "frac": achieved / peak,
-        "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+        "traffic": traffic_bytes,
+        "traffic_source": (traffic or {}).get("capture"),
         "kernel": "sos_tile_kernel<float,float,4> (32-channel x 64-sample cp.async tiles, persistent warps)",
         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SAMPLE * C * T,
         "peak_source": peak_src,

@@ -66,7 +66,7 @@ __device__ __forceinline__ int elem_offset(int r, int e) {
 }
 
 template <typename IO, typename CT, int K>
-__global__ void __launch_bounds__(kWarps * 32, kCtasPerSm)
+__global__ void __launch_bounds__(kWarps * 32, sizeof(CT) == 8 ? (kCtasPerSm + 1) / 2 : kCtasPerSm)
 sos_tile_kernel(const __grid_constant__ SosCoef<CT, K> cf, const __grid_constant__ SosCoefD<K> cd,
                 const __grid_constant__ TileGeom g) {
     using Tr = IoTraits<IO>;
