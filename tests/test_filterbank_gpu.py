@@ -25,7 +25,7 @@ def test_logfilterbank_golden_stack():
     before = _native.kernel_launches()
     y = bank(torch.from_numpy(g["x"]).to(DEV))
     torch.cuda.synchronize()
-    assert 1 <= _native.kernel_launches() - before <= 2  # one fused launch (+ optional warm-up), not 8
+    assert 1 <= _native.kernel_launches() - before <= 4  # fused launches (f32 group, f64 group, optional warm-ups), not 8
     assert y.shape == (8, 2, 4096)
     assert rel_to_max(y.cpu().numpy(), g["bank"]) < TOL
     np.testing.assert_allclose(np.stack([f._sos.numpy() for f in bank.filters]), g["bank_sos"], rtol=1e-13)

@@ -28,13 +28,16 @@ namespace {
 constexpr int kWarps = 4;
 constexpr int kStages = 3;
 constexpr int kMaxSpw = 16;  // streams per warp (LB >= 2)
-constexpr int kInBytes = kStages * kMaxSpw * kPitch;
 constexpr int kOutBytes = 32 * kPitch;
-constexpr int kTabBytes = (32 + 2 * kMaxSpw) * 8;
-constexpr int kWarpSmem = kInBytes + kOutBytes + kTabBytes;
-constexpr int kCtaSmem = kWarps * kWarpSmem;
-constexpr int kWarpsPerSm = 8;
 constexpr int kMaxKb = 4;
+constexpr int kMaxCtasPerSm = 5;  // register budget: __launch_bounds__(128, 5)
+// Shared memory of one warp depends on how many streams it serves (32 / lanes-per-stream):
+// [kStages][spw] input rows, one 32-row output tile, offset tables.
+__host__ __device__ constexpr int warp_smem_bytes(int spw) { return kStages * spw * kPitch + kOutBytes + (32 + 2 * spw) * 8; }
+inline int ctas_per_sm(int spw) {
+    const int n = kSmemPerSm / (kWarps * warp_smem_bytes(spw) + 1024);
+    return n < 1 ? 1 : (n > kMaxCtasPerSm ? kMaxCtasPerSm : n);
+}
 
 template <int KB>
 struct BankCoef {
@@ -51,6 +54,7 @@ struct BankGeom {
     double *state_x;  // [N(group), KB, C, 2] of THIS band group
     double *state_y;
     int n_bands;      // bands in this launch (<= 32)
+    int band_id[32];  // global band index of local band b (y row block and state block)
     int lb_shift;     // log2(lanes per stream)
     int mode;         // TFX_BANK_STACK / TFX_BANK_SUM
     int accumulate;   // SUM: add onto what y already holds (band groups after the first)
@@ -58,7 +62,7 @@ struct BankGeom {
 };
 
 template <typename IO, typename CT, int KB>
-__global__ void __launch_bounds__(kWarps * 32, 2)
+__global__ void __launch_bounds__(kWarps * 32, sizeof(CT) == 8 ? 3 : kMaxCtasPerSm)
 bank_stream_kernel(const __grid_constant__ BankCoef<KB> cd, const __grid_constant__ BankGeom g) {
     using Tr = IoTraits<IO>;
     using Vec = typename Tr::Vec;
@@ -71,21 +75,23 @@ bank_stream_kernel(const __grid_constant__ BankCoef<KB> cd, const __grid_constan
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    unsigned char *wsm = smem_raw + warp * kWarpSmem;
+    const int LB = 1 << g.lb_shift;
+    const int SPW = 32 >> g.lb_shift;
+    const int in_stage = SPW * kPitch;
+    unsigned char *wsm = smem_raw + warp * warp_smem_bytes(SPW);
     unsigned char *in_bufs = wsm;
-    unsigned char *out_tile = wsm + kInBytes;
-    int64_t *t_offy = reinterpret_cast<int64_t *>(wsm + kInBytes + kOutBytes);  // per lane-row
-    int64_t *t_offx = t_offy + 32;                                                // per stream slot
-    int64_t *t_len = t_offx + kMaxSpw;
+    unsigned char *out_tile = wsm + kStages * in_stage;
+    int64_t *t_offy = reinterpret_cast<int64_t *>(out_tile + kOutBytes);  // per lane-row
+    int64_t *t_offx = t_offy + 32;                                        // per stream slot
+    int64_t *t_len = t_offx + SPW;
 
     const IO *__restrict__ xg = static_cast<const IO *>(g.x);
     IO *__restrict__ yg = static_cast<IO *>(g.y);
 
-    const int LB = 1 << g.lb_shift;
-    const int SPW = 32 >> g.lb_shift;
     const int slot = lane >> g.lb_shift;
     const int band = lane & (LB - 1);
     const bool band_ok = band < g.n_bands;
+    const int64_t gband = g.band_id[band_ok ? band : 0];
 
     const int64_t q = (static_cast<int64_t>(blockIdx.x) * kWarps + warp) * SPW + slot;
     const bool live = q < g.nstreams;
@@ -126,7 +132,7 @@ bank_stream_kernel(const __grid_constant__ BankCoef<KB> cd, const __grid_constan
         if (g.state_x != nullptr) {
 #pragma unroll
             for (int k = 0; k < KB; ++k) {
-                const int64_t o = ((static_cast<int64_t>(band) * KB + k) * g.C + c) * 2;
+                const int64_t o = ((gband * KB + k) * g.C + c) * 2;
                 const double x1 = g.state_x[o], x2 = g.state_x[o + 1];
                 const double y1 = g.state_y[o], y2 = g.state_y[o + 1];
                 s1[k] = static_cast<CT>(cd.b1[band][k] * x1 + cd.b2[band][k] * x2 - cd.a1[band][k] * y1 - cd.a2[band][k] * y2);
@@ -157,7 +163,7 @@ bank_stream_kernel(const __grid_constant__ BankCoef<KB> cd, const __grid_constan
         t_offx[slot] = c * g.ldx + n0;
         t_len[slot] = len;
     }
-    t_offy[lane] = static_cast<int64_t>(band) * g.ldb + c * g.ldy + n0;
+    t_offy[lane] = gband * g.ldb + c * g.ldy + n0;
     int64_t maxlen = len;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
@@ -165,8 +171,16 @@ bank_stream_kernel(const __grid_constant__ BankCoef<KB> cd, const __grid_constan
     __syncwarp();
 
     auto issue_load = [&](int64_t i, int stage) {
-        unsigned char *buf = in_bufs + stage * (kMaxSpw * kPitch);
+        unsigned char *buf = in_bufs + stage * in_stage;
         const int64_t base = i * CH;
+        // steady state: every stream of the warp has a whole chunk left -> unconditional copies
+        if (g.vec_ok && __all_sync(0xffffffffu, len - base >= CH || len - base <= 0)) {
+            for (int idx = lane; idx < SPW * kNvec; idx += 32) {
+                const int r = idx / kNvec, piece = idx % kNvec;
+                if (t_len[r] > base) cp_async<16>(buf + r * kPitch + piece * 16, xg + t_offx[r] + base + piece * VEC);
+            }
+            return;
+        }
         for (int idx = lane; idx < SPW * kNvec; idx += 32) {
             const int r = idx / kNvec, piece = idx % kNvec;
             const int64_t rem = t_len[r] - base;
@@ -192,7 +206,7 @@ bank_stream_kernel(const __grid_constant__ BankCoef<KB> cd, const __grid_constan
     for (int64_t i = 0; i < nch; ++i) {
         cp_async_wait<kStages - 1>();
         __syncwarp();
-        const unsigned char *buf = in_bufs + stage * (kMaxSpw * kPitch);
+        const unsigned char *buf = in_bufs + stage * in_stage;
         const int64_t base = i * CH;
         const int cnt = static_cast<int>(max(static_cast<int64_t>(0), min(len - base, static_cast<int64_t>(CH))));
 
@@ -225,9 +239,19 @@ bank_stream_kernel(const __grid_constant__ BankCoef<KB> cd, const __grid_constan
 
         // ---- leave the SM as coalesced rows -----------------------------------------------
         if (!warm_pass) {
-            if (g.mode == TFX_BANK_STACK) {
+            const bool all_full = g.vec_ok && __all_sync(0xffffffffu, len - base >= CH || len - base <= 0);
+            if (g.mode == TFX_BANK_STACK && all_full) {
+                // steady state: 16 unconditional coalesced row stores (rows of absent bands / streams skipped)
                 const int piece = lane % kNvec, half = lane / kNvec;
-#pragma unroll 4
+#pragma unroll
+                for (int t = 0; t < 32 / RPI; ++t) {
+                    const int r = RPI * t + half;
+                    if ((r & (LB - 1)) < g.n_bands && t_len[r >> g.lb_shift] > base)
+                        st_stream16(yg + t_offy[r] + base + piece * VEC, *reinterpret_cast<const Vec *>(out_tile + r * kPitch + piece * 16));
+                }
+            } else if (g.mode == TFX_BANK_STACK) {
+                const int piece = lane % kNvec, half = lane / kNvec;
+#pragma unroll 1
                 for (int t = 0; t < 32 / RPI; ++t) {
                     const int r = RPI * t + half;
                     if ((r & (LB - 1)) >= g.n_bands) continue;
@@ -283,7 +307,7 @@ bank_stream_kernel(const __grid_constant__ BankCoef<KB> cd, const __grid_constan
         for (int k = 0; k < KB; ++k) {
             hx[k][0] = hx[k][1] = hy[k][0] = hy[k][1] = CT(0);
             if (mine) {
-                const int64_t o = ((static_cast<int64_t>(band) * KB + k) * g.C + c) * 2;
+                const int64_t o = ((gband * KB + k) * g.C + c) * 2;
                 hx[k][0] = static_cast<CT>(g.state_x[o]);
                 hx[k][1] = static_cast<CT>(g.state_x[o + 1]);
                 hy[k][0] = static_cast<CT>(g.state_y[o]);
@@ -308,7 +332,7 @@ bank_stream_kernel(const __grid_constant__ BankCoef<KB> cd, const __grid_constan
                 }
             }
             if (g.mode == TFX_BANK_STACK) {
-                if (act) yg[static_cast<int64_t>(band) * g.ldb + c * g.ldy + n] = static_cast<IO>(v);
+                if (act) yg[gband * g.ldb + c * g.ldy + n] = static_cast<IO>(v);
             } else {
                 // band-ordered sum, identical to the tile reduction above
                 IO acc = IO(0);
@@ -323,7 +347,7 @@ bank_stream_kernel(const __grid_constant__ BankCoef<KB> cd, const __grid_constan
         if (mine) {
 #pragma unroll
             for (int k = 0; k < KB; ++k) {
-                const int64_t o = ((static_cast<int64_t>(band) * KB + k) * g.C + c) * 2;
+                const int64_t o = ((gband * KB + k) * g.C + c) * 2;
                 g.state_x[o] = static_cast<double>(hx[k][0]);
                 g.state_x[o + 1] = static_cast<double>(hx[k][1]);
                 g.state_y[o] = static_cast<double>(hy[k][0]);
@@ -338,9 +362,10 @@ int launch_bank(const BankCoef<KB> &cd, BankGeom g, const Segmentation &seg, cud
     auto kern = bank_stream_kernel<IO, CT, KB>;
     static bool attr_set = false;
     if (!attr_set) {
-        TFX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtaSmem));
+        TFX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * warp_smem_bytes(kMaxSpw)));
         attr_set = true;
     }
+    const int kCtaSmem = kWarps * warp_smem_bytes(32 >> g.lb_shift);
     const int64_t per_cta = static_cast<int64_t>(kWarps) * (32 >> g.lb_shift);
     if (seg.S > 1) {
         BankGeom gw = g;
@@ -359,14 +384,14 @@ int launch_bank(const BankCoef<KB> &cd, BankGeom g, const Segmentation &seg, cud
 }
 
 template <typename IO, typename CT, int KB>
-int run_group(const std::vector<std::shared_ptr<const SosPlan>> &plans, int b_lo, int nb, BankGeom g,
+int run_group(const std::vector<std::shared_ptr<const SosPlan>> &plans, const int *bands, int nb, BankGeom g,
               const Segmentation &seg, cudaStream_t stream) {
     BankCoef<KB> cd;
     for (int b = 0; b < 32; ++b)
         for (int k = 0; k < KB; ++k) {
             const bool have = b < nb;
             const SosSection id{1.0, 0.0, 0.0, 0.0, 0.0};
-            const SosSection &s = have ? plans[b_lo + b]->sec[k] : id;
+            const SosSection &s = have ? plans[bands[b]]->sec[k] : id;
             cd.b0[b][k] = s.b0;
             cd.b1[b][k] = s.b1;
             cd.b2[b][k] = s.b2;
@@ -377,13 +402,13 @@ int run_group(const std::vector<std::shared_ptr<const SosPlan>> &plans, int b_lo
 }
 
 template <typename IO, typename CT>
-int run_group_kb(int KB, const std::vector<std::shared_ptr<const SosPlan>> &plans, int b_lo, int nb, const BankGeom &g,
+int run_group_kb(int KB, const std::vector<std::shared_ptr<const SosPlan>> &plans, const int *bands, int nb, const BankGeom &g,
                  const Segmentation &seg, cudaStream_t stream) {
     switch (KB) {
-        case 1: return run_group<IO, CT, 1>(plans, b_lo, nb, g, seg, stream);
-        case 2: return run_group<IO, CT, 2>(plans, b_lo, nb, g, seg, stream);
-        case 3: return run_group<IO, CT, 3>(plans, b_lo, nb, g, seg, stream);
-        case 4: return run_group<IO, CT, 4>(plans, b_lo, nb, g, seg, stream);
+        case 1: return run_group<IO, CT, 1>(plans, bands, nb, g, seg, stream);
+        case 2: return run_group<IO, CT, 2>(plans, bands, nb, g, seg, stream);
+        case 3: return run_group<IO, CT, 3>(plans, bands, nb, g, seg, stream);
+        case 4: return run_group<IO, CT, 4>(plans, bands, nb, g, seg, stream);
         default: set_error("filterbank: Kb must be in [1, %d]", kMaxKb); return TFX_EINVAL;
     }
 }
@@ -416,70 +441,91 @@ int filterbank_device(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, int
     int rc = require_device();
     if (rc != TFX_OK) return rc;
 
-    uint32_t prec = flags & TFX_PREC_MASK;
-    if (prec == TFX_PREC_AUTO) {
-        prec = TFX_PREC_F32;
-        for (auto &p : plans)
-            if (p->auto_prec == TFX_PREC_F64) prec = TFX_PREC_F64;
-    }
-    if (sizeof(IO) == 8) prec = TFX_PREC_F64;
+    // Precision per band.  With TFX_PREC_AUTO the bank is split by the per-band probe: bands whose
+    // float32 recurrence is accurate run in a float32 launch, the others (low corners) in a
+    // float64 launch -- the lanes of one launch execute one instruction stream, so mixing would
+    // make every band pay for float64.  (In SUM mode the f32 group is accumulated first; the
+    // summation order therefore differs from the reference's child order by rounding only.)
+    const uint32_t want = flags & TFX_PREC_MASK;
     const bool no_split = (flags & TFX_NO_SPLIT) != 0;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     const size_t esz = sizeof(IO);
-
-    for (int b_lo = 0; b_lo < N; b_lo += 32) {
-        const int nb = std::min(32, N - b_lo);
-        int64_t warm_needed = 0;
-        for (int b = 0; b < nb; ++b) {
-            const SosPass &p = plans[b_lo + b]->passes[0];
-            const int64_t w = prec == TFX_PREC_F32 ? p.warm_f32 : (esz == 4 ? p.warm_f64_io32 : p.warm_f64_io64);
-            if (w < 0) {
-                warm_needed = -1;
-                break;
+    std::vector<int> list32, list64;
+    for (int b = 0; b < N; ++b) {
+        uint32_t pb = want == TFX_PREC_AUTO ? static_cast<uint32_t>(plans[b]->auto_prec) : want;
+        if (esz == 8) pb = TFX_PREC_F64;
+        (pb == TFX_PREC_F32 ? list32 : list64).push_back(b);
+    }
+    // Splitting only pays when the float64 launch gets narrower (fewer lanes per stream) than the
+    // whole bank would be: otherwise one float64 launch reads x once and fills the lanes better
+    // (measured: 32 bands, 19 of them f64: 30.1 ms unsplit vs 34.7 ms split).
+    if (!list32.empty() && !list64.empty() && N <= 32 && lanes_shift(static_cast<int>(list64.size())) >= lanes_shift(N)) {
+        list64.clear();
+        list32.clear();
+        for (int b = 0; b < N; ++b) list64.push_back(b);
+    }
+    bool first_launch = true;
+    for (int pass = 0; pass < 2; ++pass) {
+        const std::vector<int> &list = pass == 0 ? list32 : list64;
+        const uint32_t prec = pass == 0 ? TFX_PREC_F32 : TFX_PREC_F64;
+        for (size_t lo = 0; lo < list.size(); lo += 32) {
+            const int nb = static_cast<int>(std::min<size_t>(32, list.size() - lo));
+            const int *bands = list.data() + lo;
+            int64_t warm_needed = 0;
+            for (int b = 0; b < nb; ++b) {
+                const SosPass &p = plans[bands[b]]->passes[0];
+                const int64_t w = prec == TFX_PREC_F32 ? p.warm_f32 : (esz == 4 ? p.warm_f64_io32 : p.warm_f64_io64);
+                if (w < 0) {
+                    warm_needed = -1;
+                    break;
+                }
+                warm_needed = std::max(warm_needed, w);
             }
-            warm_needed = std::max(warm_needed, w);
-        }
-        const int sh = lanes_shift(nb);
-        const int64_t capacity = static_cast<int64_t>(sm_count()) * kWarpsPerSm * (32 >> sh);
-        const Segmentation seg = choose_segmentation(C, T, warm_needed, capacity, no_split);
-        BankGeom g{};
-        g.x = x;
-        g.y = mode == TFX_BANK_STACK ? y + static_cast<int64_t>(b_lo) * ldb : y;
-        g.ldx = ldx;
-        g.ldy = ldy;
-        g.ldb = mode == TFX_BANK_STACK ? ldb : 0;
-        g.C = C;
-        g.T = T;
-        g.S = seg.S;
-        g.Lseg = seg.Lseg;
-        g.ws = workspace;
-        g.ws_stride = C * seg.S;
-        g.state_x = state_x ? state_x + static_cast<int64_t>(b_lo) * Kb * C * 2 : nullptr;
-        g.state_y = state_y ? state_y + static_cast<int64_t>(b_lo) * Kb * C * 2 : nullptr;
-        g.n_bands = nb;
-        g.lb_shift = sh;
-        g.mode = mode;
-        g.accumulate = (mode == TFX_BANK_SUM && b_lo > 0) ? 1 : 0;
-        g.vec_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0) &&
-                   ((ldx * esz) % 16 == 0) && ((ldy * esz) % 16 == 0) && ((g.ldb * esz) % 16 == 0) &&
-                   (seg.S == 1 || (seg.Lseg * esz) % 16 == 0);
-        if (seg.S > 1) {
-            const size_t need = static_cast<size_t>(2 * Kb * nb) * static_cast<size_t>(C * seg.S) * (prec == TFX_PREC_F32 ? 4 : 8);
-            if (workspace == nullptr || workspace_bytes < need) {
-                set_error("filterbank: workspace of %zu bytes needed, %zu given (query tfx_filterbank_workspace_bytes)", need,
-                          workspace_bytes);
-                return TFX_EWORKSPACE;
+            const int sh = lanes_shift(nb);
+            const int spw = 32 >> sh;
+            const int64_t capacity = static_cast<int64_t>(sm_count()) * ctas_per_sm(spw) * kWarps * spw;
+            const Segmentation seg = choose_segmentation(C, T, warm_needed, capacity, no_split);
+            BankGeom g{};
+            g.x = x;
+            g.y = y;
+            g.ldx = ldx;
+            g.ldy = ldy;
+            g.ldb = mode == TFX_BANK_STACK ? ldb : 0;
+            g.C = C;
+            g.T = T;
+            g.S = seg.S;
+            g.Lseg = seg.Lseg;
+            g.ws = workspace;
+            g.ws_stride = C * seg.S;
+            g.state_x = state_x;
+            g.state_y = state_y;
+            g.n_bands = nb;
+            for (int b = 0; b < 32; ++b) g.band_id[b] = bands[b < nb ? b : 0];
+            g.lb_shift = sh;
+            g.mode = mode;
+            g.accumulate = (mode == TFX_BANK_SUM && !first_launch) ? 1 : 0;
+            g.vec_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0) &&
+                       ((ldx * esz) % 16 == 0) && ((ldy * esz) % 16 == 0) && ((g.ldb * esz) % 16 == 0) &&
+                       (seg.S == 1 || (seg.Lseg * esz) % 16 == 0);
+            if (seg.S > 1) {
+                const size_t need = static_cast<size_t>(2 * Kb * nb) * static_cast<size_t>(C * seg.S) * (prec == TFX_PREC_F32 ? 4 : 8);
+                if (workspace == nullptr || workspace_bytes < need) {
+                    set_error("filterbank: workspace of %zu bytes needed, %zu given (query tfx_filterbank_workspace_bytes)", need,
+                              workspace_bytes);
+                    return TFX_EWORKSPACE;
+                }
             }
+            if (prec == TFX_PREC_F32) {
+                if constexpr (sizeof(IO) == 4)
+                    rc = run_group_kb<IO, float>(Kb, plans, bands, nb, g, seg, stream);
+                else
+                    rc = TFX_EINVAL;
+            } else {
+                rc = run_group_kb<IO, double>(Kb, plans, bands, nb, g, seg, stream);
+            }
+            if (rc != TFX_OK) return rc;
+            first_launch = false;
         }
-        if (prec == TFX_PREC_F32) {
-            if constexpr (sizeof(IO) == 4)
-                rc = run_group_kb<IO, float>(Kb, plans, b_lo, nb, g, seg, stream);
-            else
-                rc = TFX_EINVAL;
-        } else {
-            rc = run_group_kb<IO, double>(Kb, plans, b_lo, nb, g, seg, stream);
-        }
-        if (rc != TFX_OK) return rc;
     }
     return TFX_OK;
 }
@@ -493,7 +539,7 @@ size_t tfx_filterbank_workspace_bytes(int64_t C, int64_t T, int N, int Kb) {
     (void)T;
     if (C <= 0 || N <= 0 || Kb <= 0) return 0;
     // S > 1 only when C*S fits one wave of streams (at most SMs*8*16 with 2 lanes per stream).
-    const int64_t streams = static_cast<int64_t>(tfx::sm_count()) * tfx::kWarpsPerSm * tfx::kMaxSpw + 128;
+    const int64_t streams = static_cast<int64_t>(tfx::sm_count()) * tfx::kMaxCtasPerSm * tfx::kWarps * tfx::kMaxSpw + 128;
     const int nb = N < 32 ? N : 32;
     return static_cast<size_t>(2 * Kb * nb) * static_cast<size_t>(streams) * 8 + 256;
 }

@@ -109,33 +109,74 @@ __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // a * conj(b)
     return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
 }
 
-// forward, decimation in frequency: natural order in, base-4 digit-reversed order out
+// The transform is three radix-16 passes (two radix-4 stages fused in registers per pass), one
+// radix-16 butterfly per thread per pass: 3 shared-memory round trips instead of 6.  Logical
+// index i lives at i + (i >> 4) (one pad slot per 16) so that the stride-1, stride-16 and
+// stride-256 accesses of the three passes are all (nearly) bank-conflict free.
+constexpr int kPadN = kN + kN / 16;
+__device__ __forceinline__ int pidx(int i) { return i + (i >> 4); }
+
+// radix-4 DIF butterfly on registers; twiddles applied to outputs 1..3 (w1, w2, w3)
+__device__ __forceinline__ void bfly4_dif(float2 &a, float2 &b, float2 &c, float2 &d, bool tw, float2 w1, float2 w2, float2 w3) {
+    const float2 t0 = make_float2(a.x + c.x, a.y + c.y), t1 = make_float2(a.x - c.x, a.y - c.y);
+    const float2 t2 = make_float2(b.x + d.x, b.y + d.y);
+    const float2 t3 = make_float2(b.y - d.y, -(b.x - d.x));  // (b - d) * (-i)
+    a = make_float2(t0.x + t2.x, t0.y + t2.y);
+    float2 y1 = make_float2(t1.x + t3.x, t1.y + t3.y);
+    float2 y2 = make_float2(t0.x - t2.x, t0.y - t2.y);
+    float2 y3 = make_float2(t1.x - t3.x, t1.y - t3.y);
+    if (tw) {
+        y1 = cmul(y1, w1);
+        y2 = cmul(y2, w2);
+        y3 = cmul(y3, w3);
+    }
+    b = y1;
+    c = y2;
+    d = y3;
+}
+// radix-4 DIT (inverse) butterfly on registers; conjugate twiddles applied to inputs 1..3
+__device__ __forceinline__ void bfly4_dit_inv(float2 &a, float2 &b, float2 &c, float2 &d, bool tw, float2 w1, float2 w2, float2 w3) {
+    if (tw) {
+        b = cmulc(b, w1);
+        c = cmulc(c, w2);
+        d = cmulc(d, w3);
+    }
+    const float2 t0 = make_float2(a.x + c.x, a.y + c.y), t1 = make_float2(a.x - c.x, a.y - c.y);
+    const float2 t2 = make_float2(b.x + d.x, b.y + d.y);
+    const float2 t3 = make_float2(-(b.y - d.y), b.x - d.x);  // (b - d) * (+i)
+    a = make_float2(t0.x + t2.x, t0.y + t2.y);
+    b = make_float2(t1.x + t3.x, t1.y + t3.y);
+    c = make_float2(t0.x - t2.x, t0.y - t2.y);
+    d = make_float2(t1.x - t3.x, t1.y - t3.y);
+}
+
+// forward, decimation in frequency: natural order in, base-4 digit-reversed order out.
+// Pass with stride q (= 256, 16, 1) fuses the radix-4 stages of quarter 4q and q.
 __device__ void fft_dif4(float2 *s, const float2 *__restrict__ tw) {
 #pragma unroll 1
-    for (int lq = 10; lq >= 0; lq -= 2) {  // q = 4^5 .. 1
+    for (int lq = 8; lq >= 0; lq -= 4) {
         const int q = 1 << lq;
+        const int j = threadIdx.x & (q - 1);
+        const int base = ((threadIdx.x >> lq) << (lq + 4)) + j;
+        float2 v[16];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int bidx = threadIdx.x + kFftThreads * u;
-            const int j = bidx & (q - 1);
-            const int i0 = ((bidx >> lq) << (lq + 2)) + j;
-            const float2 a = s[i0], b = s[i0 + q], c = s[i0 + 2 * q], d = s[i0 + 3 * q];
-            const float2 t0 = make_float2(a.x + c.x, a.y + c.y), t1 = make_float2(a.x - c.x, a.y - c.y);
-            const float2 t2 = make_float2(b.x + d.x, b.y + d.y);
-            const float2 t3 = make_float2(b.y - d.y, -(b.x - d.x));  // (b - d) * (-i)
-            float2 y0 = make_float2(t0.x + t2.x, t0.y + t2.y), y1 = make_float2(t1.x + t3.x, t1.y + t3.y);
-            float2 y2 = make_float2(t0.x - t2.x, t0.y - t2.y), y3 = make_float2(t1.x - t3.x, t1.y - t3.y);
-            if (lq > 0) {
-                const int t = j << (10 - lq);  // j * N / (4q)
-                y1 = cmul(y1, __ldg(&tw[t]));
-                y2 = cmul(y2, __ldg(&tw[2 * t]));
-                y3 = cmul(y3, __ldg(&tw[3 * t]));
-            }
-            s[i0] = y0;
-            s[i0 + q] = y1;
-            s[i0 + 2 * q] = y2;
-            s[i0 + 3 * q] = y3;
+        for (int m = 0; m < 16; ++m) v[m] = s[pidx(base + m * q)];
+        // stage A: quarter 4q, butterflies (m, m+4, m+8, m+12), position jj = j + m*q
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int t = (j + m * q) << (8 - lq);  // jj * N / (16q)
+            bfly4_dif(v[m], v[m + 4], v[m + 8], v[m + 12], true, __ldg(&tw[t]), __ldg(&tw[2 * t]), __ldg(&tw[3 * t]));
         }
+        // stage B: quarter q, butterflies (4a, 4a+1, 4a+2, 4a+3), position j
+        const int tb = j << (10 - lq);  // j * N / (4q)
+        const bool twb = lq > 0;
+        const float2 w1 = twb ? __ldg(&tw[tb]) : make_float2(1.f, 0.f);
+        const float2 w2 = twb ? __ldg(&tw[2 * tb]) : make_float2(1.f, 0.f);
+        const float2 w3 = twb ? __ldg(&tw[3 * tb]) : make_float2(1.f, 0.f);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) bfly4_dif(v[4 * a], v[4 * a + 1], v[4 * a + 2], v[4 * a + 3], twb, w1, w2, w3);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) s[pidx(base + m * q)] = v[m];
         __syncthreads();
     }
 }
@@ -143,28 +184,28 @@ __device__ void fft_dif4(float2 *s, const float2 *__restrict__ tw) {
 // inverse (unscaled), decimation in time: digit-reversed order in, natural order out
 __device__ void fft_dit4_inv(float2 *s, const float2 *__restrict__ tw) {
 #pragma unroll 1
-    for (int lq = 0; lq <= 10; lq += 2) {
+    for (int lq = 0; lq <= 8; lq += 4) {
         const int q = 1 << lq;
+        const int j = threadIdx.x & (q - 1);
+        const int base = ((threadIdx.x >> lq) << (lq + 4)) + j;
+        float2 v[16];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int bidx = threadIdx.x + kFftThreads * u;
-            const int j = bidx & (q - 1);
-            const int i0 = ((bidx >> lq) << (lq + 2)) + j;
-            float2 a = s[i0], b = s[i0 + q], c = s[i0 + 2 * q], d = s[i0 + 3 * q];
-            if (lq > 0) {
-                const int t = j << (10 - lq);
-                b = cmulc(b, __ldg(&tw[t]));
-                c = cmulc(c, __ldg(&tw[2 * t]));
-                d = cmulc(d, __ldg(&tw[3 * t]));
-            }
-            const float2 t0 = make_float2(a.x + c.x, a.y + c.y), t1 = make_float2(a.x - c.x, a.y - c.y);
-            const float2 t2 = make_float2(b.x + d.x, b.y + d.y);
-            const float2 t3 = make_float2(-(b.y - d.y), b.x - d.x);  // (b - d) * (+i)
-            s[i0] = make_float2(t0.x + t2.x, t0.y + t2.y);
-            s[i0 + q] = make_float2(t1.x + t3.x, t1.y + t3.y);
-            s[i0 + 2 * q] = make_float2(t0.x - t2.x, t0.y - t2.y);
-            s[i0 + 3 * q] = make_float2(t1.x - t3.x, t1.y - t3.y);
+        for (int m = 0; m < 16; ++m) v[m] = s[pidx(base + m * q)];
+        // stage B first (quarter q), then stage A (quarter 4q): the mirror of the forward pass
+        const int tb = j << (10 - lq);
+        const bool twb = lq > 0;
+        const float2 w1 = twb ? __ldg(&tw[tb]) : make_float2(1.f, 0.f);
+        const float2 w2 = twb ? __ldg(&tw[2 * tb]) : make_float2(1.f, 0.f);
+        const float2 w3 = twb ? __ldg(&tw[3 * tb]) : make_float2(1.f, 0.f);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) bfly4_dit_inv(v[4 * a], v[4 * a + 1], v[4 * a + 2], v[4 * a + 3], twb, w1, w2, w3);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int t = (j + m * q) << (8 - lq);
+            bfly4_dit_inv(v[m], v[m + 4], v[m + 8], v[m + 12], true, __ldg(&tw[t]), __ldg(&tw[2 * t]), __ldg(&tw[3 * t]));
         }
+#pragma unroll
+        for (int m = 0; m < 16; ++m) s[pidx(base + m * q)] = v[m];
         __syncthreads();
     }
 }
@@ -181,23 +222,23 @@ __global__ void fir_twiddle_kernel(float2 *tw) {
 // H[p] = DIF-FFT(taps[pB:(p+1)B] zero-padded to N), one CTA per partition
 __global__ void __launch_bounds__(kFftThreads) fir_taps_fft_kernel(const float *__restrict__ taps, int64_t K, float2 *__restrict__ H,
                                                                   const float2 *__restrict__ tw) {
-    __shared__ float2 s[kN];
+    __shared__ float2 s[kPadN];
     const int64_t p = blockIdx.x;
     for (int i = threadIdx.x; i < kN; i += kFftThreads) {
         const int64_t j = p * kB + i;
-        s[i] = make_float2((i < kB && j < K) ? taps[j] : 0.f, 0.f);
+        s[pidx(i)] = make_float2((i < kB && j < K) ? taps[j] : 0.f, 0.f);
     }
     __syncthreads();
     fft_dif4(s, tw);
     float2 *out = H + p * kN;
-    for (int i = threadIdx.x; i < kN; i += kFftThreads) out[i] = s[i];
+    for (int i = threadIdx.x; i < kN; i += kFftThreads) out[i] = s[pidx(i)];
 }
 
 // Z[pair][row] = DIF-FFT(x_a[(k-1)B : (k+1)B] + i x_b[...]),  k = k_first + row (k < 0 -> zeros)
 __global__ void __launch_bounds__(kFftThreads) fir_fwd_kernel(const float *__restrict__ x, int64_t C, int64_t T, int64_t ldx,
                                                              int64_t k_first, int64_t nrows, float2 *__restrict__ Z,
                                                              const float2 *__restrict__ tw) {
-    __shared__ float2 s[kN];
+    __shared__ float2 s[kPadN];
     const int64_t row = blockIdx.x;
     const int64_t pair = blockIdx.y;
     const int64_t k = k_first + row;
@@ -213,11 +254,11 @@ __global__ void __launch_bounds__(kFftThreads) fir_fwd_kernel(const float *__res
     for (int i = threadIdx.x; i < kN; i += kFftThreads) {
         const int64_t n = nbase + i;
         const bool ok = n >= 0 && n < T;
-        s[i] = make_float2(ok ? xa[n] : 0.f, (ok && cb < C) ? xb[n] : 0.f);
+        s[pidx(i)] = make_float2(ok ? xa[n] : 0.f, (ok && cb < C) ? xb[n] : 0.f);
     }
     __syncthreads();
     fft_dif4(s, tw);
-    for (int i = threadIdx.x; i < kN; i += kFftThreads) out[i] = s[i];
+    for (int i = threadIdx.x; i < kN; i += kFftThreads) out[i] = s[pidx(i)];
 }
 
 // Y[pair][j] = sum_p H[p] . Z[pair][j + (P-1) - p],  j in [0, nout)
@@ -283,11 +324,11 @@ __global__ void __launch_bounds__(512) fir_mac_kernel(const float2 *__restrict__
 __global__ void __launch_bounds__(kFftThreads) fir_inv_kernel(const float2 *__restrict__ Y, float *__restrict__ y, int64_t C, int64_t T,
                                                              int64_t ldy, int64_t k_first, int64_t nout,
                                                              const float2 *__restrict__ tw) {
-    __shared__ float2 s[kN];
+    __shared__ float2 s[kPadN];
     const int64_t j = blockIdx.x;
     const int64_t pair = blockIdx.y;
     const float2 *in = Y + (pair * nout + j) * kN;
-    for (int i = threadIdx.x; i < kN; i += kFftThreads) s[i] = in[i];
+    for (int i = threadIdx.x; i < kN; i += kFftThreads) s[pidx(i)] = in[i];
     __syncthreads();
     fft_dit4_inv(s, tw);
     const int64_t ca = 2 * pair, cb = 2 * pair + 1;
@@ -296,7 +337,7 @@ __global__ void __launch_bounds__(kFftThreads) fir_inv_kernel(const float2 *__re
     for (int i = threadIdx.x; i < kB; i += kFftThreads) {
         const int64_t n = nbase + i;
         if (n < T) {
-            const float2 v = s[kB + i];
+            const float2 v = s[pidx(kB + i)];
             y[ca * ldy + n] = v.x * scale;
             if (cb < C) y[cb * ldy + n] = v.y * scale;
         }
