@@ -11,7 +11,7 @@ namespace tfx {
 
 constexpr size_t kWsHeader = 256;  // workspace header (work counter)
 #ifndef TFX_OVERSUB
-#define TFX_OVERSUB 8
+#define TFX_OVERSUB 16
 #endif
 constexpr int kOversub = TFX_OVERSUB;  // work items per resident warp when the signal is long enough
 

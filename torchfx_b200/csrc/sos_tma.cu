@@ -20,7 +20,6 @@
 // base pointers and row pitches, T < 2^31, enough channels to fill the lanes.
 #include <algorithm>
 #include <cstdint>
-#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -109,7 +108,6 @@ struct TmaGeom {
     int64_t ws_stride;
     double *state_x;
     double *state_y;
-    int debug;  // developer experiments only (TFX_DEBUG): 1 = skip stores, 2 = skip loads after the first
 };
 
 template <typename IO>
@@ -200,10 +198,6 @@ sos_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const int32_t row0 = static_cast<int32_t>(grp * 32);
     auto issue_load = [&](int64_t i, int stage) {  // lane 0 only
         unsigned char *tile = ring + stage * kTileBytes;
-        if ((g.debug & 2) && i >= kStages) {  // experiment: no global reads, just complete the barrier
-            mbar_arrive_expect_tx(&bars[stage], 0);
-            return;
-        }
         const int32_t col = static_cast<int32_t>(n0 + i * CH);
         mbar_arrive_expect_tx(&bars[stage], kTileBytes);
         tma_load_2d(tile, &map_x, col, row0, &bars[stage]);
@@ -288,7 +282,7 @@ sos_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         if (!warm_pass) {
             fence_proxy_async_smem();  // my STS must be visible to the TMA store
             __syncwarp();
-            if (lane == 0 && !(g.debug & 1)) {
+            if (lane == 0) {
                 const int32_t col = static_cast<int32_t>(n0 + base);
                 tma_store_2d(&map_y, col, row0, tile);
                 tma_store_2d(&map_y, col + CH / 2, row0, tile + 4096);
@@ -416,8 +410,6 @@ int launch_tma_pass(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, int64
     g.ws_stride = C * seg.S;
     g.state_x = state_x;
     g.state_y = state_y;
-    static const int dbg = getenv("TFX_DEBUG") ? atoi(getenv("TFX_DEBUG")) : 0;
-    g.debug = dbg;
     return launch_tma_any<IO, CT>(sec, k, mx, my, g, seg, stream);
 }
 
