@@ -151,3 +151,56 @@ def test_packed_ffma2_kernel_matches(K):
     wa, _, _ = oracle.sos_cascade(xa[:4], sos)
     ya, _, _, _ = run(xa, sos, precision="f32", packed=True, no_tma=True)
     assert rel_to_max(ya[:4], wa) < TOL_F32
+
+
+# ---- channel-tile kernel (sos_tile.cu), the default for many channels -------------------------------
+@pytest.mark.parametrize("shape", [(32, 1), (32, 2), (32, 3), (64, 63), (64, 64), (64, 65), (96, 129), (128, 1000), (52, 260),
+                                   (27, 2052), (33, 4099), (100, 777)])
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_tile_kernel_short_ragged_with_state(shape, precision):
+    """Default kernel for >= 26 channels: T around one and two chunks (tracked tail), odd T
+    (unaligned rows -> element-wise copies), half-empty channel groups, DF1 state in and out."""
+    rng = np.random.default_rng(sum(shape) + 7)
+    x = rng.standard_normal(shape).astype(np.float32)
+    sos = sps.cheby1(4, 1.0, 0.3, output="sos")
+    sx0 = rng.standard_normal((2, shape[0], 2))
+    sy0 = rng.standard_normal((2, shape[0], 2))
+    want, wsx, wsy = oracle.sos_cascade(x, sos, sx0, sy0)
+    y, sx, sy, _ = run(x, sos, sx0.copy(), sy0.copy(), precision=precision, no_tma=True)
+    tol = TOL_F32 if precision == "f32" else TOL_F64REC
+    assert rel_to_max(y, want) < tol
+    np.testing.assert_allclose(sx, wsx, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(sy, wsy, rtol=1e-4, atol=tol * 10 * max(np.abs(wsy).max(), 1.0))
+
+
+@pytest.mark.parametrize("K", [1, 3, 4, 8, 11, 16])
+def test_tile_kernel_section_counts_and_f64_io(K):
+    rng = np.random.default_rng(900 + K)
+    x = rng.standard_normal((40, 30000))
+    sos = sps.butter(2 * K, 0.23, output="sos")
+    want, wsx, wsy = oracle.sos_cascade(x, sos)
+    y, sx, sy, _ = run(x, sos, no_tma=True)  # float64 I/O through the tile kernel
+    np.testing.assert_allclose(y, want, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(sy, wsy, rtol=1e-8, atol=1e-10)
+    xf = x.astype(np.float32)
+    wf, _, _ = oracle.sos_cascade(xf, sos)
+    yf, _, _, _ = run(xf, sos, precision="f32", no_tma=True)
+    assert rel_to_max(yf, wf) < TOL_F32
+
+
+def test_tile_kernel_chunked_in_place_strided_view():
+    rng = np.random.default_rng(77)
+    big = torch.from_numpy((0.1 * rng.standard_normal((70, 120000))).astype(np.float32)).to(DEV)
+    view = big[3:67, 64:100064]  # 64 channels, row stride 120000, aligned start
+    x_np = view.cpu().numpy().copy()
+    sos_np = sps.butter(8, 5000 / 24000, output="sos")
+    sos = torch.from_numpy(sos_np)
+    want, _, wsy = oracle.sos_cascade(x_np, sos_np)
+    sx = torch.zeros(4, 64, 2, dtype=torch.float64, device=DEV)
+    sy = torch.zeros_like(sx)
+    for lo, hi in ((0, 40000), (40000, 40004), (40004, 100000)):
+        blk = view[:, lo:hi]
+        _ops.sos_cascade_(blk, sos, sx, sy, out=blk, no_tma=True)
+    assert rel_to_max(view.cpu().numpy(), want) < TOL_F32
+    np.testing.assert_allclose(sy.cpu().numpy(), wsy, rtol=1e-3, atol=1e-5 * np.abs(wsy).max())
+    assert torch.equal(big[0], torch.from_numpy((0.1 * np.random.default_rng(77).standard_normal((70, 120000))).astype(np.float32))[0].to(DEV))
