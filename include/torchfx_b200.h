@@ -123,6 +123,12 @@ int tfx_sos_cascade_uses_tma(const void *x, const void *y, int64_t C, int64_t T,
 /* What TFX_PREC_AUTO resolves to for this cascade: returns TFX_PREC_F32 or TFX_PREC_F64,
  * and (optionally) the probe's estimated f32 round-off relative to max|y|.               */
 int tfx_sos_auto_precision(const double *sos_host, int K, double *probe_rel_err);
+/* When the policy above answers TFX_PREC_F64: the sections (bit k = section k) that have to
+ * run the float64 recurrence for the probe error to fall under the bound; the remaining
+ * sections keep the float32 recurrence in the mixed-precision channel-tile kernel.  All K
+ * bits set = no proper subset suffices (the whole cascade runs in float64).  0 for cascades
+ * whose policy is TFX_PREC_F32.                                                          */
+uint64_t tfx_sos_mixed_mask(const double *sos_host, int K, double *mixed_rel_err);
 
 /* Host twins (HOST pointers, OpenMP over channels, f64 DF1 -- the arithmetic of the
  * reference's CPU kernel cpu/iir_cpu.cpp:64-159).  This is device dispatch, mirroring

@@ -96,3 +96,25 @@ def test_auto_precision_policy():
     hp = torch.from_numpy(sps.butter(2, 20 / 24000, btype="highpass", output="sos")).contiguous()
     assert lib.tfx_sos_auto_precision(hp.data_ptr(), 1, ctypes.byref(err)) == _native.TFX_PREC_F64
     assert err.value > 2e-6
+
+
+def test_mixed_precision_mask_policy():
+    """cfg4 chain: only the ParametricEQ section needs the float64 recurrence."""
+    import torchfx_b200 as fx
+
+    lib = _native.load()
+    err = ctypes.c_double()
+    chain = [fx.filter.LoButterworth(5000, order=4, fs=48000), fx.filter.ParametricEQ(1000, q=2.0, gain=3.0, fs=48000),
+             fx.filter.HiShelving(8000, q=0.707, gain=2.0, gain_scale="db", fs=48000)]
+    for f in chain:
+        f.compute_coefficients()
+    sos = torch.cat([f._sos for f in chain]).contiguous()
+    assert lib.tfx_sos_auto_precision(sos.data_ptr(), 4, None) == _native.TFX_PREC_F64
+    mask = lib.tfx_sos_mixed_mask(sos.data_ptr(), 4, ctypes.byref(err))
+    assert mask == 0b0100 and 0 < err.value <= 2e-6
+    import scipy.signal as sps
+
+    lp = torch.from_numpy(sps.butter(8, 5000 / 24000, output="sos")).contiguous()
+    assert lib.tfx_sos_mixed_mask(lp.data_ptr(), 4, None) == 0  # float32 everywhere
+    hp = torch.from_numpy(sps.butter(4, 20 / 24000, btype="highpass", output="sos")).contiguous()
+    assert lib.tfx_sos_mixed_mask(hp.data_ptr(), 2, None) == 0b11  # no proper subset suffices

@@ -204,3 +204,30 @@ def test_tile_kernel_chunked_in_place_strided_view():
     assert rel_to_max(view.cpu().numpy(), want) < TOL_F32
     np.testing.assert_allclose(sy.cpu().numpy(), wsy, rtol=1e-3, atol=1e-5 * np.abs(wsy).max())
     assert torch.equal(big[0], torch.from_numpy((0.1 * np.random.default_rng(77).standard_normal((70, 120000))).astype(np.float32))[0].to(DEV))
+
+
+def test_mixed_precision_chain_cfg4():
+    """TFX_PREC_AUTO on LoButterworth | ParametricEQ | HiShelving: float64 only in the EQ section
+    (mixed-precision tile kernel); must meet the float64-recurrence tolerance, with state carry."""
+    import torchfx_b200 as fx
+
+    chain = [fx.filter.LoButterworth(5000, order=4, fs=48000), fx.filter.ParametricEQ(1000, q=2.0, gain=3.0, fs=48000),
+             fx.filter.HiShelving(8000, q=0.707, gain=2.0, gain_scale="db", fs=48000)]
+    for f in chain:
+        f.compute_coefficients()
+    sos = np.vstack([f._sos.numpy() for f in chain])
+    rng = np.random.default_rng(4)
+    x = (0.1 * rng.standard_normal((64, 400001))).astype(np.float32)[:, :400000]
+    sx0 = 0.1 * rng.standard_normal((4, 64, 2))
+    sy0 = 0.1 * rng.standard_normal((4, 64, 2))
+    want, wsx, wsy = oracle.sos_cascade(x, sos, sx0, sy0)
+    y, sx, sy, _ = run(x, sos, sx0.copy(), sy0.copy(), precision="auto", force_tma=False)
+    assert rel_to_max(y, want) < 2e-6
+    np.testing.assert_allclose(sx, wsx, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(sy, wsy, rtol=1e-4, atol=1e-5 * np.abs(wsy).max())
+    # chunked == contiguous
+    xt = torch.from_numpy(x).to(DEV)
+    stx = torch.from_numpy(sx0).to(DEV)
+    sty = torch.from_numpy(sy0).to(DEV)
+    parts = [_ops.sos_cascade_(xt[:, lo:hi], torch.from_numpy(sos), stx, sty) for lo, hi in ((0, 100000), (100000, 100001), (100001, 400000))]
+    assert rel_to_max(torch.cat(parts, 1).cpu().numpy(), want) < 2e-6

@@ -42,6 +42,7 @@ _SIGNATURES = {
     "tfx_sos_cascade_f32": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int, _P, _P, c_uint32, _P, c_size_t, _P]),
     "tfx_sos_cascade_f64": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int, _P, _P, c_uint32, _P, c_size_t, _P]),
     "tfx_sos_auto_precision": (c_int, [_P, c_int, _P]),
+    "tfx_sos_mixed_mask": (c_uint64, [_P, c_int, _P]),
     "tfx_sos_cascade_uses_tma": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int]),
     "tfx_sos_cascade_cpu_f32": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int, _P, _P]),
     "tfx_sos_cascade_cpu_f64": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int, _P, _P]),

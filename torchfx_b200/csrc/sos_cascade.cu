@@ -422,6 +422,32 @@ int sos_cascade_device(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, in
         const int64_t warm_needed = prec == TFX_PREC_F32 ? p.warm_f32 : (sizeof(IO) == 4 ? p.warm_f64_io32 : p.warm_f64_io64);
         const IO *px = pi == 0 ? x : y;
         const int64_t pldx = pi == 0 ? ldx : ldy;
+        // TFX_PREC_AUTO picked float64 but only some sections need it: mixed-precision tile kernel
+        if constexpr (sizeof(IO) == 4) {
+            const unsigned local_mask = static_cast<unsigned>((plan->mixed_mask >> p.k0) & ((1ull << p.k) - 1ull));
+            const bool mixed = (flags & TFX_PREC_MASK) == TFX_PREC_AUTO && plan->auto_prec == TFX_PREC_F64 && !(flags & TFX_NO_TILE) &&
+                               !(flags & TFX_FORCE_TMA) && tile_path_ok(C) && (local_mask == 0u || tile_mixed_supported(p.k, local_mask));
+            if (mixed) {
+                const int64_t lanes = (C + 31) / 32 * 32;
+                const Segmentation seg = choose_segmentation(lanes, T, p.warm_f64_io32, tile_stream_capacity(), no_split, kOversub);
+                if (seg.S > 1) {
+                    const size_t need = kWsHeader + static_cast<size_t>(2 * p.k) * static_cast<size_t>(C * seg.S) * 8;
+                    if (workspace == nullptr || workspace_bytes < need) {
+                        set_error("sos cascade: workspace of %zu bytes needed, %zu given (query tfx_sos_cascade_workspace_bytes)", need,
+                                  workspace_bytes);
+                        return TFX_EWORKSPACE;
+                    }
+                }
+                double *psx = state_x ? state_x + static_cast<int64_t>(p.k0) * C * 2 : nullptr;
+                double *psy = state_y ? state_y + static_cast<int64_t>(p.k0) * C * 2 : nullptr;
+                if (local_mask == 0u)
+                    rc = launch_tile_pass<float, float>(px, y, C, T, pldx, ldy, plan->sec.data() + p.k0, p.k, seg, workspace, psx, psy, stream);
+                else
+                    rc = launch_tile_pass_mixed(px, y, C, T, pldx, ldy, plan->sec.data() + p.k0, p.k, local_mask, seg, workspace, psx, psy, stream);
+                if (rc != TFX_OK) return rc;
+                continue;
+            }
+        }
         if (want_tma(flags, prec, p.k) && tma_path_ok(px, y, C, T, pldx, ldy, sizeof(IO))) {
             // TMA-tiled kernel: a warp is 32 consecutive channels, so segments are counted per
             // channel GROUP (capacity / 32 warps in one wave).
@@ -546,6 +572,13 @@ int tfx_sos_cascade_f64(const double *x, double *y, int64_t C, int64_t T, int64_
                         void *workspace, size_t workspace_bytes, void *stream) {
     return tfx::sos_cascade_device<double>(x, y, C, T, ldx, ldy, sos_host, K, state_x, state_y, flags, workspace,
                                            workspace_bytes, stream);
+}
+
+uint64_t tfx_sos_mixed_mask(const double *sos_host, int K, double *mixed_rel_err) {
+    auto plan = tfx::get_sos_plan(sos_host, K);
+    if (!plan) return 0;
+    if (mixed_rel_err) *mixed_rel_err = plan->mixed_rel_err;
+    return plan->auto_prec == TFX_PREC_F64 ? plan->mixed_mask : 0;
 }
 
 int tfx_sos_cascade_uses_tma(const void *x, const void *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, int elem_bytes) {

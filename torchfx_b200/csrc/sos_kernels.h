@@ -45,6 +45,12 @@ template <typename IO, typename CT>
 int launch_tile_pass(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, const SosSection *sec, int k,
                      const Segmentation &seg, void *ws_base, double *state_x, double *state_y, cudaStream_t stream);
 
+// Mixed precision: float32 recurrence, float64 only in the sections of `f64_mask` (bit k = section k).
+bool tile_mixed_supported(int k, unsigned f64_mask);
+int launch_tile_pass_mixed(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, const SosSection *sec, int k,
+                           unsigned f64_mask, const Segmentation &seg, void *ws_base, double *state_x, double *state_y,
+                           cudaStream_t stream);
+
 // TMA-tiled kernel (sos_tma.cu): lanes = 32 consecutive channels.
 bool tma_path_ok(const void *x, const void *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, int elem_bytes);
 int64_t tma_stream_capacity();  // streams (lanes) resident in one wave

@@ -174,6 +174,75 @@ void probe_precision(SosPlan &plan) {
     plan.auto_prec = plan.probe_rel_err <= kAutoF32Bound ? TFX_PREC_F32 : TFX_PREC_F64;
 }
 
+// Probe of the mixed-precision recurrence the tile kernel runs (sos_tile.cu, Cascade<MixedF>):
+// sections in `mask` in float64 with a float32 signal in and out, the others in float32.
+double probe_mixed(const SosPlan &plan, uint64_t mask, int len) {
+    const int K = plan.K;
+    std::vector<double> sx0(K, 0.0), sx1(K, 0.0), sy0(K, 0.0), sy1(K, 0.0), d1(K, 0.0), d2(K, 0.0);
+    std::vector<float> f1(K, 0.f), f2(K, 0.f);
+    uint64_t lcg = 0x9E3779B97F4A7C15ull;
+    double max_y = 0.0, max_err = 0.0;
+    for (int n = 0; n < len; ++n) {
+        lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+        const float xf = static_cast<float>(static_cast<double>(static_cast<int64_t>(lcg >> 11)) * (1.0 / 4503599627370496.0) - 1.0);
+        double v = xf;
+        for (int k = 0; k < K; ++k) {
+            const SosSection &c = plan.sec[k];
+            const double y = c.b0 * v + c.b1 * sx0[k] + c.b2 * sx1[k] - c.a1 * sy0[k] - c.a2 * sy1[k];
+            sx1[k] = sx0[k];
+            sx0[k] = v;
+            sy1[k] = sy0[k];
+            sy0[k] = y;
+            v = y;
+        }
+        float u = xf;
+        for (int k = 0; k < K; ++k) {
+            const SosSection &c = plan.sec[k];
+            if ((mask >> k) & 1ull) {
+                const double ud = u;
+                const double y = std::fma(c.b0, ud, d1[k]);
+                d1[k] = std::fma(-c.a1, y, std::fma(c.b1, ud, d2[k]));
+                d2[k] = std::fma(-c.a2, y, c.b2 * ud);
+                u = static_cast<float>(y);
+            } else {
+                const float b0 = static_cast<float>(c.b0), b1 = static_cast<float>(c.b1), b2 = static_cast<float>(c.b2);
+                const float na1 = static_cast<float>(-c.a1), na2 = static_cast<float>(-c.a2);
+                const float y = std::fmaf(b0, u, f1[k]);
+                f1[k] = std::fmaf(na1, y, std::fmaf(b1, u, f2[k]));
+                f2[k] = std::fmaf(na2, y, b2 * u);
+                u = y;
+            }
+        }
+        if (!std::isfinite(v) || !std::isfinite(u)) return INFINITY;
+        max_y = std::max(max_y, std::fabs(v));
+        max_err = std::max(max_err, std::fabs(static_cast<double>(u) - v));
+    }
+    return max_y > 0.0 ? max_err / max_y : 0.0;
+}
+
+// Which sections have to be float64?  Rank the sections by how much promoting each one alone
+// helps, then promote in that order until the cascade meets the bound.
+void choose_mixed_mask(SosPlan &plan) {
+    const int K = plan.K;
+    const uint64_t full = K >= 64 ? ~0ull : ((1ull << K) - 1ull);
+    plan.mixed_mask = full;
+    plan.mixed_rel_err = 0.0;
+    if (plan.auto_prec != TFX_PREC_F64 || K < 2 || K > 16 || !std::isfinite(plan.probe_rel_err)) return;
+    std::vector<std::pair<double, int>> gain;
+    for (int k = 0; k < K; ++k) gain.push_back({probe_mixed(plan, 1ull << k, kProbeLen / 2), k});
+    std::sort(gain.begin(), gain.end());  // promoting this section alone leaves the smallest error -> first
+    uint64_t mask = 0;
+    for (int i = 0; i < K - 1; ++i) {
+        mask |= 1ull << gain[i].second;
+        const double err = probe_mixed(plan, mask, kProbeLen);
+        if (err <= kAutoF32Bound) {
+            plan.mixed_mask = mask;
+            plan.mixed_rel_err = err;
+            return;
+        }
+    }
+}
+
 struct Cache {
     std::mutex mu;
     std::list<std::string> order;  // most recent first
@@ -222,6 +291,7 @@ std::shared_ptr<const SosPlan> get_sos_plan(const double *sos_host, int K) {
         plan->passes.push_back(p);
     }
     probe_precision(*plan);
+    choose_mixed_mask(*plan);
     {
         std::lock_guard<std::mutex> lk(c.mu);
         auto it = c.map.find(key);

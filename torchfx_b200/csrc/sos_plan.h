@@ -32,6 +32,11 @@ struct SosPlan {
     std::vector<SosPass> passes;
     int auto_prec = 0;        // TFX_PREC_F32 or TFX_PREC_F64
     double probe_rel_err = 0;  // max|y_f32 - y_f64| / max|y_f64| on the probe signal
+    // When auto_prec == F64: the smallest set of sections (bit k = section k) that must run the
+    // float64 recurrence for the probe error to fall under the bound; the others may stay
+    // float32 (mixed-precision kernel).  All ones when no proper subset suffices.
+    uint64_t mixed_mask = 0;
+    double mixed_rel_err = 0;
 };
 
 // Cached by the coefficient bytes (thread-safe).  Returns nullptr and sets the error

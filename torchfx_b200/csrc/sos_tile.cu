@@ -19,6 +19,7 @@
 // counter; segment start states come from a warm-up launch (see sos_plan.cpp).
 #include <algorithm>
 #include <cstdint>
+#include <type_traits>
 
 #include "common.cuh"
 #include "sos_kernels.h"
@@ -55,6 +56,7 @@ struct TileGeom {
     double *state_y;
     unsigned long long *counter;  // NULL: item = global warp id
     int vec_ok;
+    unsigned f64_mask;  // MixedF only: sections that run the float64 recurrence
 };
 
 // byte offset of the 16-byte column v (0..15) of row r inside a swizzled tile
@@ -65,10 +67,129 @@ __device__ __forceinline__ int elem_offset(int r, int e) {
     return col_offset(r, e / EPV) + (e % EPV) * static_cast<int>(sizeof(IO));
 }
 
+// Compute-type tag: float32 recurrence except for the sections flagged in TileGeom::f64_mask,
+// which run in float64 (float32 signal in and out of each such section).  Lets a chain like
+// LoButterworth | ParametricEQ | HiShelving pay for float64 only in the one section whose
+// float32 round-off would break the 1e-5 bar (sos_plan.cpp picks the mask with a probe).
+template <unsigned MASK>
+struct MixedF {};  // MASK is a compile-time constant: a run-time per-section branch costs more than float64 everywhere
+
+template <typename CT>
+struct CtTraits {
+    using Coef = CT;   // element type of the SosCoef kernel parameter
+    using Store = CT;  // element type of the workspace / tracked history
+    static constexpr bool heavy = sizeof(CT) == 8;
+};
+template <unsigned MASK>
+struct CtTraits<MixedF<MASK>> {
+    using Coef = float;
+    using Store = double;
+    static constexpr bool heavy = false;
+};
+
+// DF2T state of one stream + the recurrence, uniform precision
+template <typename CT, int K>
+struct Cascade {
+    CT s1[K], s2[K];
+    __device__ __forceinline__ void set(int k, double a, double b) {
+        s1[k] = static_cast<CT>(a);
+        s2[k] = static_cast<CT>(b);
+    }
+    __device__ __forceinline__ CT get1(int k) const { return s1[k]; }
+    __device__ __forceinline__ CT get2(int k) const { return s2[k]; }
+    template <typename IO>
+    __device__ __forceinline__ IO step(const SosCoef<CT, K> &cf, const SosCoefD<K> &, unsigned, IO x) {
+        return static_cast<IO>(sos_step<CT, K>(cf, s1, s2, static_cast<CT>(x)));
+    }
+    // one sample, recording every section's input / output (DF1 history)
+    template <typename IO>
+    __device__ __forceinline__ IO step_tracked(const SosCoef<CT, K> &cf, const SosCoefD<K> &, unsigned, IO x, CT (&hx)[K][2],
+                                               CT (&hy)[K][2]) {
+        CT v = static_cast<CT>(x);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const CT y = fma_rn(cf.b0[k], v, s1[k]);
+            s1[k] = fma_rn(cf.na1[k], y, fma_rn(cf.b1[k], v, s2[k]));
+            s2[k] = fma_rn(cf.na2[k], y, cf.b2[k] * v);
+            hx[k][1] = hx[k][0];
+            hx[k][0] = v;
+            hy[k][1] = hy[k][0];
+            hy[k][0] = y;
+            v = y;
+        }
+        return static_cast<IO>(v);
+    }
+};
+
+// mixed precision: per-section float32 or float64 state, float32 signal between sections
+template <unsigned MASK, int K>
+struct Cascade<MixedF<MASK>, K> {
+    float f1[K], f2[K];
+    double d1[K], d2[K];
+    __device__ __forceinline__ void set(int k, double a, double b) {
+        f1[k] = static_cast<float>(a);
+        f2[k] = static_cast<float>(b);
+        d1[k] = a;
+        d2[k] = b;
+    }
+    __device__ __forceinline__ double get1(int k) const { return d1[k]; }
+    __device__ __forceinline__ double get2(int k) const { return d2[k]; }
+    __device__ __forceinline__ void sync_views() {  // keep get1/get2 meaningful for f32 sections
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (!((MASK >> k) & 1u)) {
+                d1[k] = f1[k];
+                d2[k] = f2[k];
+            }
+    }
+    __device__ __forceinline__ float section(const SosCoef<float, K> &cf, const SosCoefD<K> &cd, unsigned, int k, float v,
+                                             double &xin, double &yout) {
+        if ((MASK >> k) & 1u) {  // folds at compile time once the section loop is unrolled
+            const double vd = static_cast<double>(v);
+            const double y = __fma_rn(cd.b0[k], vd, d1[k]);
+            d1[k] = __fma_rn(-cd.a1[k], y, __fma_rn(cd.b1[k], vd, d2[k]));
+            d2[k] = __fma_rn(-cd.a2[k], y, cd.b2[k] * vd);
+            xin = vd;
+            yout = y;
+            return static_cast<float>(y);
+        }
+        const float y = __fmaf_rn(cf.b0[k], v, f1[k]);
+        f1[k] = __fmaf_rn(cf.na1[k], y, __fmaf_rn(cf.b1[k], v, f2[k]));
+        f2[k] = __fmaf_rn(cf.na2[k], y, cf.b2[k] * v);
+        xin = v;
+        yout = y;
+        return y;
+    }
+    template <typename IO>
+    __device__ __forceinline__ IO step(const SosCoef<float, K> &cf, const SosCoefD<K> &cd, unsigned mask, IO x) {
+        float v = static_cast<float>(x);
+        double a, b;
+#pragma unroll
+        for (int k = 0; k < K; ++k) v = section(cf, cd, mask, k, v, a, b);
+        return static_cast<IO>(v);
+    }
+    template <typename IO>
+    __device__ __forceinline__ IO step_tracked(const SosCoef<float, K> &cf, const SosCoefD<K> &cd, unsigned mask, IO x,
+                                               double (&hx)[K][2], double (&hy)[K][2]) {
+        float v = static_cast<float>(x);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double a, b;
+            v = section(cf, cd, mask, k, v, a, b);
+            hx[k][1] = hx[k][0];
+            hx[k][0] = a;
+            hy[k][1] = hy[k][0];
+            hy[k][0] = b;
+        }
+        return static_cast<IO>(v);
+    }
+};
+
 template <typename IO, typename CT, int K>
-__global__ void __launch_bounds__(kWarps * 32, sizeof(CT) == 8 ? (kCtasPerSm + 1) / 2 : kCtasPerSm)
-sos_tile_kernel(const __grid_constant__ SosCoef<CT, K> cf, const __grid_constant__ SosCoefD<K> cd,
+__global__ void __launch_bounds__(kWarps * 32, CtTraits<CT>::heavy ? (kCtasPerSm + 1) / 2 : kCtasPerSm)
+sos_tile_kernel(const __grid_constant__ SosCoef<typename CtTraits<CT>::Coef, K> cf, const __grid_constant__ SosCoefD<K> cd,
                 const __grid_constant__ TileGeom g) {
+    using Store = typename CtTraits<CT>::Store;
     using Tr = IoTraits<IO>;
     using Vec = typename Tr::Vec;
     constexpr int VEC = Tr::VEC;
@@ -119,12 +240,9 @@ sos_tile_kernel(const __grid_constant__ SosCoef<CT, K> cf, const __grid_constant
         const int64_t nch = (len + CH - 1) / CH;
 
         // ---- start state (DF2T) ----------------------------------------------------------------
-        CT s1[K], s2[K];
+        Cascade<CT, K> st;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            s1[k] = CT(0);
-            s2[k] = CT(0);
-        }
+        for (int k = 0; k < K; ++k) st.set(k, 0.0, 0.0);
         if (live) {
             if (from_true_state) {
                 if (g.state_x != nullptr) {
@@ -133,17 +251,13 @@ sos_tile_kernel(const __grid_constant__ SosCoef<CT, K> cf, const __grid_constant
                         const int64_t o = (static_cast<int64_t>(k) * g.C + c) * 2;
                         const double x1 = g.state_x[o], x2 = g.state_x[o + 1];
                         const double y1 = g.state_y[o], y2 = g.state_y[o + 1];
-                        s1[k] = static_cast<CT>(cd.b1[k] * x1 + cd.b2[k] * x2 - cd.a1[k] * y1 - cd.a2[k] * y2);
-                        s2[k] = static_cast<CT>(cd.b2[k] * x1 - cd.a2[k] * y1);
+                        st.set(k, cd.b1[k] * x1 + cd.b2[k] * x2 - cd.a1[k] * y1 - cd.a2[k] * y2, cd.b2[k] * x1 - cd.a2[k] * y1);
                     }
                 }
             } else if (!warm_pass) {
-                const CT *wsp = static_cast<const CT *>(g.ws) + (c * g.S + j);
+                const Store *wsp = static_cast<const Store *>(g.ws) + (c * g.S + j);
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    s1[k] = wsp[(2 * k) * g.ws_stride];
-                    s2[k] = wsp[(2 * k + 1) * g.ws_stride];
-                }
+                for (int k = 0; k < K; ++k) st.set(k, wsp[(2 * k) * g.ws_stride], wsp[(2 * k + 1) * g.ws_stride]);
             }
         }
 
@@ -181,17 +295,17 @@ sos_tile_kernel(const __grid_constant__ SosCoef<CT, K> cf, const __grid_constant
         }
 
         // DF1 history of every section, only maintained over the channel's last two chunks
-        CT hx[K][2], hy[K][2];
+        Store hx[K][2], hy[K][2];
         if (do_tail) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                hx[k][0] = hx[k][1] = hy[k][0] = hy[k][1] = CT(0);
+                hx[k][0] = hx[k][1] = hy[k][0] = hy[k][1] = Store(0);
                 if (live && from_true_state) {  // consulted only when fewer than two samples are filtered (then S == 1)
                     const int64_t o = (static_cast<int64_t>(k) * g.C + c) * 2;
-                    hx[k][0] = static_cast<CT>(g.state_x[o]);
-                    hx[k][1] = static_cast<CT>(g.state_x[o + 1]);
-                    hy[k][0] = static_cast<CT>(g.state_y[o]);
-                    hy[k][1] = static_cast<CT>(g.state_y[o + 1]);
+                    hx[k][0] = static_cast<Store>(g.state_x[o]);
+                    hx[k][1] = static_cast<Store>(g.state_x[o + 1]);
+                    hy[k][0] = static_cast<Store>(g.state_y[o]);
+                    hy[k][1] = static_cast<Store>(g.state_y[o + 1]);
                 }
             }
         }
@@ -212,30 +326,23 @@ sos_tile_kernel(const __grid_constant__ SosCoef<CT, K> cf, const __grid_constant
                     for (int v = 0; v < 16; ++v) {
                         Vec *p = reinterpret_cast<Vec *>(tile + col_offset(lane, v));
                         Vec a = *p;
-                        filter_vec<CT, K>(cf, s1, s2, a);
+                        a.x = st.step(cf, cd, g.f64_mask, a.x);
+                        a.y = st.step(cf, cd, g.f64_mask, a.y);
+                        if constexpr (VEC == 4) {
+                            a.z = st.step(cf, cd, g.f64_mask, a.z);
+                            a.w = st.step(cf, cd, g.f64_mask, a.w);
+                        }
                         *p = a;
                     }
                 } else if (!tracked) {
                     for (int e = 0; e < cnt; ++e) {
                         IO *p = reinterpret_cast<IO *>(tile + elem_offset<IO>(lane, e));
-                        *p = static_cast<IO>(sos_step<CT, K>(cf, s1, s2, static_cast<CT>(*p)));
+                        *p = st.step(cf, cd, g.f64_mask, *p);
                     }
                 } else {
                     for (int e = 0; e < cnt; ++e) {
                         IO *p = reinterpret_cast<IO *>(tile + elem_offset<IO>(lane, e));
-                        CT v = static_cast<CT>(*p);
-#pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            const CT y = fma_rn(cf.b0[k], v, s1[k]);
-                            s1[k] = fma_rn(cf.na1[k], y, fma_rn(cf.b1[k], v, s2[k]));
-                            s2[k] = fma_rn(cf.na2[k], y, cf.b2[k] * v);
-                            hx[k][1] = hx[k][0];
-                            hx[k][0] = v;
-                            hy[k][1] = hy[k][0];
-                            hy[k][0] = y;
-                            v = y;
-                        }
-                        *p = static_cast<IO>(v);
+                        *p = st.step_tracked(cf, cd, g.f64_mask, *p, hx, hy);
                     }
                 }
             }
@@ -272,11 +379,12 @@ sos_tile_kernel(const __grid_constant__ SosCoef<CT, K> cf, const __grid_constant
 
         if (live) {
             if (warm_pass) {
-                CT *wsp = static_cast<CT *>(g.ws) + (c * g.S + j);
+                if constexpr (!std::is_floating_point<CT>::value) st.sync_views();
+                Store *wsp = static_cast<Store *>(g.ws) + (c * g.S + j);
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    wsp[(2 * k) * g.ws_stride] = s1[k];
-                    wsp[(2 * k + 1) * g.ws_stride] = s2[k];
+                    wsp[(2 * k) * g.ws_stride] = st.get1(k);
+                    wsp[(2 * k + 1) * g.ws_stride] = st.get2(k);
                 }
             } else if (do_tail) {
 #pragma unroll
@@ -296,14 +404,15 @@ sos_tile_kernel(const __grid_constant__ SosCoef<CT, K> cf, const __grid_constant
 
 template <typename IO, typename CT, int K>
 int launch_tile_k(const SosSection *sec, TileGeom g, const Segmentation &seg, unsigned long long *counter, cudaStream_t stream) {
-    SosCoef<CT, K> cf;
+    using CoefT = typename CtTraits<CT>::Coef;
+    SosCoef<CoefT, K> cf;
     SosCoefD<K> cd;
     for (int k = 0; k < K; ++k) {
-        cf.b0[k] = static_cast<CT>(sec[k].b0);
-        cf.b1[k] = static_cast<CT>(sec[k].b1);
-        cf.b2[k] = static_cast<CT>(sec[k].b2);
-        cf.na1[k] = static_cast<CT>(-sec[k].a1);
-        cf.na2[k] = static_cast<CT>(-sec[k].a2);
+        cf.b0[k] = static_cast<CoefT>(sec[k].b0);
+        cf.b1[k] = static_cast<CoefT>(sec[k].b1);
+        cf.b2[k] = static_cast<CoefT>(sec[k].b2);
+        cf.na1[k] = static_cast<CoefT>(-sec[k].a1);
+        cf.na2[k] = static_cast<CoefT>(-sec[k].a2);
         cd.b0[k] = sec[k].b0;
         cd.b1[k] = sec[k].b1;
         cd.b2[k] = sec[k].b2;
@@ -387,6 +496,41 @@ int launch_tile_pass(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, int6
                ((ldy * esz) % 16 == 0);
     return launch_tile_any<IO, CT>(sec, k, g, seg, static_cast<unsigned long long *>(ws_base), stream);
 }
+
+int launch_tile_pass_mixed(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, const SosSection *sec, int k,
+                           unsigned f64_mask, const Segmentation &seg, void *ws_base, double *state_x, double *state_y,
+                           cudaStream_t stream) {
+    TileGeom g{};
+    g.x = x;
+    g.y = y;
+    g.ldx = ldx;
+    g.ldy = ldy;
+    g.C = C;
+    g.T = T;
+    g.S = seg.S;
+    g.Lseg = seg.Lseg;
+    g.G = (C + 31) / 32;
+    g.ws = ws_base ? static_cast<unsigned char *>(ws_base) + kWsHeader : nullptr;
+    g.ws_stride = C * seg.S;
+    g.state_x = state_x;
+    g.state_y = state_y;
+    g.f64_mask = f64_mask;
+    g.vec_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0) && ((ldx * 4) % 16 == 0) &&
+               ((ldy * 4) % 16 == 0);
+    unsigned long long *counter = static_cast<unsigned long long *>(ws_base);
+#define TFX_MIXED_CASE(KK, MM) \
+    if (k == KK && f64_mask == MM) return launch_tile_k<float, MixedF<MM>, KK>(sec, g, seg, counter, stream);
+    TFX_MIXED_CASE(2, 1u) TFX_MIXED_CASE(2, 2u)
+    TFX_MIXED_CASE(3, 1u) TFX_MIXED_CASE(3, 2u) TFX_MIXED_CASE(3, 3u) TFX_MIXED_CASE(3, 4u) TFX_MIXED_CASE(3, 5u) TFX_MIXED_CASE(3, 6u)
+    TFX_MIXED_CASE(4, 1u) TFX_MIXED_CASE(4, 2u) TFX_MIXED_CASE(4, 3u) TFX_MIXED_CASE(4, 4u) TFX_MIXED_CASE(4, 5u) TFX_MIXED_CASE(4, 6u)
+    TFX_MIXED_CASE(4, 7u) TFX_MIXED_CASE(4, 8u) TFX_MIXED_CASE(4, 9u) TFX_MIXED_CASE(4, 10u) TFX_MIXED_CASE(4, 11u)
+    TFX_MIXED_CASE(4, 12u) TFX_MIXED_CASE(4, 13u) TFX_MIXED_CASE(4, 14u)
+#undef TFX_MIXED_CASE
+    set_error("internal: no mixed-precision kernel for K=%d mask=%u", k, f64_mask);
+    return TFX_EINVAL;
+}
+
+bool tile_mixed_supported(int k, unsigned f64_mask) { return k >= 2 && k <= 4 && f64_mask != 0u && f64_mask != (1u << k) - 1u; }
 
 template int launch_tile_pass<float, float>(const float *, float *, int64_t, int64_t, int64_t, int64_t, const SosSection *, int,
                                             const Segmentation &, void *, double *, double *, cudaStream_t);
