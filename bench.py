@@ -63,61 +63,107 @@ def recorded_traffic():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clock / power / throttle reasons of one GPU WHILE the timed region runs.
 
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    NVML from a Python thread every ~5 ms (the timed region can be as short as 0.1 s at 8 GPUs;
+    `nvidia-smi -lms` is too coarse for that); falls back to an nvidia-smi subprocess when
+    pynvml is unavailable.  CUDA calls made by the main thread release the GIL."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
     def __init__(self, gpu_index: int):
         self.gpu_index = gpu_index
-        self.rows: list[list[str]] = []
-        self.proc = None
-        self.thread = None
+        self.samples: list[tuple[float, float, int]] = []
+        self.sm_max = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+        self._handle = None
+        self._smi = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # NVML enumerates physical GPUs; honour CUDA_VISIBLE_DEVICES when it is a list of indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if gpu_index < len(ids) and ids[gpu_index].isdigit():
+                    phys = int(ids[gpu_index])
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
+
+    def _loop(self):
+        nv = self._nvml
+        while not self._stop.is_set():
+            try:
+                clk = float(nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self._handle) / 1000.0
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._handle))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle))
+                self.samples.append((clk, pw, rs))
+            except Exception:
+                pass
+            self._stop.wait(0.005)
 
     def start(self):
+        if self._nvml is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+            return
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu_index)],
+            self._smi = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu_index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
-            self.proc = None
-            return
-        def pump():
-            for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
-        self.thread = threading.Thread(target=pump, daemon=True)
-        self.thread.start()
+            self._smi = None
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self._nvml is not None:
+            self._stop.set()
+            if self._thread is not None:
+                self._thread.join(timeout=2)
+            sm = [c for c, _, _ in self.samples]
+            reasons = set()
+            for _, _, rs in self.samples:
+                for bit, name in self.REASONS.items():
+                    if rs & bit:
+                        reasons.add(name)
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.sm_max,
+                    "power_w_max": max((p for _, p, _ in self.samples), default=None), "samples": len(sm),
+                    "reasons": sorted(reasons), "source": "nvml, 5 ms period, timed region only"}
+        if self._smi is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["clock sampling unavailable"]}
+        self._smi.terminate()
         try:
-            self.proc.wait(timeout=5)
+            out = self._smi.communicate(timeout=5)[0]
         except Exception:
-            self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
+            self._smi.kill()
+            out = ""
+        sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) < 8:
+        for line in out.splitlines():
+            r = [c.strip() for c in line.split(",")]
+            if len(r) < 7:
                 continue
             try:
-                sm.append(float(r[1]))
-                smax.append(float(r[2]))
-                power.append(float(r[3]))
+                sm.append(float(r[0])); smax.append(float(r[1])); power.append(float(r[2]))
             except ValueError:
                 continue
-            for name, val in zip(names, r[4:8]):
+            for name, val in zip(names, r[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {
-            "sm_mhz": statistics.median(sm) if sm else None,
-            "sm_max_mhz": max(smax) if smax else None,
-            "power_w_max": max(power) if power else None,
-            "samples": len(sm),
-            "reasons": sorted(reasons),
-        }
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvidia-smi -lms 20, timed region only"}
 
 
 def reference_cpu_step(ext, x32, sos_t):

@@ -21,6 +21,8 @@ void count_launch(int n = 1);
 int require_device();
 // SM count of the current device (cached per device id).
 int sm_count();
+// Index of the current device, clamped to [0, 64): slot for per-device one-time setup flags.
+int device_slot();
 
 #define TFX_CUDA_TRY(expr)                                                        \
     do {                                                                          \
@@ -34,6 +36,18 @@ int sm_count();
             ::tfx::set_error(__VA_ARGS__);    \
             return TFX_EINVAL;                \
         }                                     \
+    } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (function, device): do it once per
+// device for the kernel instantiation this macro is expanded in (racing threads set the same value).
+#define TFX_ENSURE_SMEM(kern, bytes)                                                                          \
+    do {                                                                                                     \
+        static bool done__[64] = {};                                                                         \
+        const int slot__ = ::tfx::device_slot();                                                             \
+        if (!done__[slot__]) {                                                                               \
+            TFX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes)));  \
+            done__[slot__] = true;                                                                           \
+        }                                                                                                    \
     } while (0)
 
 // Checks the launch that was just issued.

@@ -360,11 +360,7 @@ bank_stream_kernel(const __grid_constant__ BankCoef<KB> cd, const __grid_constan
 template <typename IO, typename CT, int KB>
 int launch_bank(const BankCoef<KB> &cd, BankGeom g, const Segmentation &seg, cudaStream_t stream) {
     auto kern = bank_stream_kernel<IO, CT, KB>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        TFX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kWarps * warp_smem_bytes(kMaxSpw)));
-        attr_set = true;
-    }
+    TFX_ENSURE_SMEM(kern, kWarps * warp_smem_bytes(kMaxSpw));
     const int kCtaSmem = kWarps * warp_smem_bytes(32 >> g.lb_shift);
     const int64_t per_cta = static_cast<int64_t>(kWarps) * (32 >> g.lb_shift);
     if (seg.S > 1) {

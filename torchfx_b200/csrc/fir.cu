@@ -429,12 +429,8 @@ int tfx_fir_f32(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int
     TFX_CHECK_LAUNCH("fir_twiddle_kernel");
     fir_taps_fft_kernel<<<static_cast<unsigned>(L.P), kFftThreads, 0, stream>>>(taps, K, H, tw);
     TFX_CHECK_LAUNCH("fir_taps_fft_kernel");
-    static bool attr_set = false;
     const size_t mac_smem = sizeof(float2) * (kMacRows + kMacPc) * kMacBins;
-    if (!attr_set) {
-        TFX_CUDA_TRY(cudaFuncSetAttribute(fir_mac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(mac_smem)));
-        attr_set = true;
-    }
+    TFX_ENSURE_SMEM(fir_mac_kernel, static_cast<int>(mac_smem));
     for (int64_t k0 = 0; k0 < L.nblk; k0 += L.slab) {
         const int64_t nout = std::min<int64_t>(L.slab, L.nblk - k0);
         const int64_t nrows = nout + L.P - 1;

@@ -42,6 +42,15 @@ int require_device() {
     return TFX_OK;
 }
 
+int device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return dev < 0 ? 0 : (dev > 63 ? 63 : dev);
+}
+
 int sm_count() {
     static std::mutex mu;
     static int cached[64];

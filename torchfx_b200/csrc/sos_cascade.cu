@@ -340,11 +340,7 @@ int launch_k(const SosSection *sec, Geom g, const Segmentation &seg, cudaStream_
         cd.a2[k] = sec[k].a2;
     }
     auto kern = sos_stream_kernel<IO, CT, K>;
-    static bool attr_set = false;  // per instantiation; racing threads set the same value
-    if (!attr_set) {
-        TFX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtaSmem));
-        attr_set = true;
-    }
+    TFX_ENSURE_SMEM(kern, kCtaSmem);
     const int64_t per_cta = kWarps * 32;
     if (seg.S > 1) {
         Geom gw = g;

@@ -393,11 +393,7 @@ int launch_pair_k(const SosSection *sec, Geom g, const Segmentation &seg, cudaSt
         cd.a2[k] = sec[k].a2;
     }
     auto kern = sos_pair_kernel<K>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        TFX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtaSmem));
-        attr_set = true;
-    }
+    TFX_ENSURE_SMEM(kern, kCtaSmem);
     const int64_t per_cta = static_cast<int64_t>(kWarps) * kRows;
     if (seg.S > 1) {
         Geom gw = g;

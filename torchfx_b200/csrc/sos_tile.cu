@@ -420,11 +420,7 @@ int launch_tile_k(const SosSection *sec, TileGeom g, const Segmentation &seg, un
         cd.a2[k] = sec[k].a2;
     }
     auto kern = sos_tile_kernel<IO, CT, K>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        TFX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtaSmem));
-        attr_set = true;
-    }
+    TFX_ENSURE_SMEM(kern, kCtaSmem);
     if (seg.S > 1) {
         TileGeom gw = g;
         gw.warm = seg.warm;

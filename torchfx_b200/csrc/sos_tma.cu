@@ -338,11 +338,7 @@ int launch_tma_k(const SosSection *sec, const CUtensorMap &mx, const CUtensorMap
         cd.a2[k] = sec[k].a2;
     }
     auto kern = sos_tma_kernel<IO, CT, K>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        TFX_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtaSmem));
-        attr_set = true;
-    }
+    TFX_ENSURE_SMEM(kern, kCtaSmem);
     if (seg.S > 1) {
         TmaGeom gw = g;
         gw.warm = seg.warm;
