@@ -239,3 +239,51 @@ def test_host_streaming_driver_matches_oracle():
     assert rel_to_max(y.numpy(), want) < TOL_F32
     np.testing.assert_allclose(sx.numpy(), wsx, rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(sy.numpy(), wsy, rtol=1e-3, atol=1e-5 * np.abs(wsy).max())
+
+
+def test_unaligned_rows_are_repitched_and_match():
+    """Odd T with many channels: the Python layer re-pitches once instead of taking the
+    element-wise kernel path; result and state must be unchanged, input untouched."""
+    rng = np.random.default_rng(41)
+    x = (0.1 * rng.standard_normal((64, 100003))).astype(np.float32)
+    sos = sps.butter(8, 5000 / 24000, output="sos")
+    want, wsx, wsy = oracle.sos_cascade(x, sos)
+    xt = torch.from_numpy(x).to(DEV)
+    sx = torch.zeros(4, 64, 2, dtype=torch.float64, device=DEV)
+    sy = torch.zeros_like(sx)
+    y = _ops.sos_cascade_(xt, torch.from_numpy(sos), sx, sy)
+    assert y.shape == (64, 100003) and torch.equal(xt.cpu(), torch.from_numpy(x))
+    assert rel_to_max(y.cpu().numpy(), want) < TOL_F32
+    np.testing.assert_allclose(sy.cpu().numpy(), wsy, rtol=1e-3, atol=1e-5 * np.abs(wsy).max())
+    # explicit out= keeps the direct (element-wise) path
+    out = torch.empty_like(xt)
+    y2 = _ops.sos_cascade_(xt, torch.from_numpy(sos), None, None, out=out)
+    assert y2 is out and rel_to_max(out.cpu().numpy(), want) < TOL_F32
+
+
+def test_config2_scale_long_run_drift():
+    """BASELINE configs[1] at a quarter of its length (1024 ch x 7.2 M samples, 29.5 GB, in place):
+    8 seeded-random channels are checked against the oracle over the FULL length (long-run
+    drift of the segmented float32 recurrence), plus the final DF1 state of those channels."""
+    free, _ = torch.cuda.mem_get_info()
+    C, T = 1024, 7_200_000
+    if free < C * T * 4 * 1.2:
+        pytest.skip("not enough free HBM")
+    g = torch.Generator(device=DEV).manual_seed(1234)
+    x = torch.empty((C, T), device=DEV)
+    x.normal_(0.0, 0.1, generator=g)
+    pick = sorted(np.random.default_rng(2).choice(C, size=8, replace=False).tolist())
+    x_pick = x[pick].cpu().numpy()
+    sos_np = sps.butter(8, 5000 / 24000, output="sos")
+    sx = torch.zeros(4, C, 2, dtype=torch.float64, device=DEV)
+    sy = torch.zeros_like(sx)
+    before = _native.kernel_launches()
+    _ops.sos_cascade_(x, torch.from_numpy(sos_np), sx, sy, out=x)
+    torch.cuda.synchronize()
+    assert _native.kernel_launches() - before == 2
+    want, wsx, wsy = oracle.sos_cascade(x_pick, sos_np)
+    assert rel_to_max(x[pick].cpu().numpy(), want) < TOL_F32
+    np.testing.assert_allclose(sy[:, pick].cpu().numpy(), wsy, rtol=1e-3, atol=1e-5 * np.abs(wsy).max())
+    np.testing.assert_allclose(sx[:, pick].cpu().numpy(), wsx, rtol=1e-3, atol=1e-5 * np.abs(wsx).max())
+    del x
+    torch.cuda.empty_cache()

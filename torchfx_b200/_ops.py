@@ -83,6 +83,11 @@ def _rows(x: Tensor) -> Tensor:
     return x
 
 
+def _rows_aligned(x: Tensor, ld: int) -> bool:
+    es = x.element_size()
+    return x.data_ptr() % 16 == 0 and (ld * es) % 16 == 0
+
+
 def _compute_dtype(x: Tensor) -> torch.dtype:
     return x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32
 
@@ -128,6 +133,17 @@ def sos_cascade_(
     ldx = xw.stride(0) if C > 1 else max(T, 1)
     ldy = y.stride(0) if C > 1 else max(T, 1)
     suffix = "f32" if cd == torch.float32 else "f64"
+    if xw.is_cuda and out is None and C > 1 and T >= 1024 and not _rows_aligned(xw, ldx):
+        # Rows that do not start on 16-byte boundaries (odd T, sliced views) would take the
+        # kernels' element-wise copy path (~3.5x slower).  Re-pitch once into a buffer whose row
+        # stride is a multiple of 16 bytes (a plain strided copy: plumbing), filter in place there
+        # and hand back the [C, T] view of it.
+        vec = 16 // xw.element_size()
+        ldp = (T + vec - 1) // vec * vec
+        buf = torch.empty((C, ldp), dtype=cd, device=xw.device)
+        y = buf[:, :T]
+        y.copy_(xw)
+        xw, ldx, ldy = y, ldp, ldp
     if xw.is_cuda:
         flags = (_PRECISIONS[precision or _default_precision] | (N.TFX_NO_SPLIT if no_split else 0)
                  | (N.TFX_NO_TMA if no_tma else 0) | (N.TFX_FORCE_TMA if force_tma else 0) | (N.TFX_PACKED if packed else 0) | (N.TFX_NO_TILE if no_tile else 0))

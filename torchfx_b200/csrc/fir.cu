@@ -150,6 +150,25 @@ __device__ __forceinline__ void bfly4_dit_inv(float2 &a, float2 &b, float2 &c, f
     d = make_float2(t1.x - t3.x, t1.y - t3.y);
 }
 
+// W_16^k = exp(-2*pi*i*k/16).  Stage-A twiddles factor as W_{16q}^{(j + m q) r} = W_{16q}^{j r} * W_16^{m r}:
+// three table loads per pass instead of twelve, the rest are these compile-time constants.
+__device__ __forceinline__ float2 w16(int k) {
+    constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
+    switch (k & 15) {
+        case 0: return make_float2(1.f, 0.f);
+        case 1: return make_float2(c1, -s1);
+        case 2: return make_float2(h, -h);
+        case 3: return make_float2(s1, -c1);
+        case 4: return make_float2(0.f, -1.f);
+        case 5: return make_float2(-s1, -c1);
+        case 6: return make_float2(-h, -h);
+        case 7: return make_float2(-c1, -s1);
+        case 8: return make_float2(-1.f, 0.f);
+        case 9: return make_float2(-c1, s1);
+        default: return make_float2(0.f, 0.f);  // 10..15 never needed (m, r <= 3)
+    }
+}
+
 // forward, decimation in frequency: natural order in, base-4 digit-reversed order out.
 // Pass with stride q (= 256, 16, 1) fuses the radix-4 stages of quarter 4q and q.
 __device__ void fft_dif4(float2 *s, const float2 *__restrict__ tw) {
@@ -158,21 +177,22 @@ __device__ void fft_dif4(float2 *s, const float2 *__restrict__ tw) {
         const int q = 1 << lq;
         const int j = threadIdx.x & (q - 1);
         const int base = ((threadIdx.x >> lq) << (lq + 4)) + j;
+        // twiddle loads first (global, L1/L2): their latency overlaps the shared-memory loads
+        const bool twb = lq > 0;
+        const int ta = j << (8 - lq);   // j * N / (16q)
+        const int tb = j << (10 - lq);  // j * N / (4q)
+        const float2 one = make_float2(1.f, 0.f);
+        const float2 a1 = twb ? __ldg(&tw[ta]) : one, a2 = twb ? __ldg(&tw[2 * ta]) : one, a3 = twb ? __ldg(&tw[3 * ta]) : one;
+        const float2 w1 = twb ? __ldg(&tw[tb]) : one, w2 = twb ? __ldg(&tw[2 * tb]) : one, w3 = twb ? __ldg(&tw[3 * tb]) : one;
         float2 v[16];
 #pragma unroll
         for (int m = 0; m < 16; ++m) v[m] = s[pidx(base + m * q)];
         // stage A: quarter 4q, butterflies (m, m+4, m+8, m+12), position jj = j + m*q
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const int t = (j + m * q) << (8 - lq);  // jj * N / (16q)
-            bfly4_dif(v[m], v[m + 4], v[m + 8], v[m + 12], true, __ldg(&tw[t]), __ldg(&tw[2 * t]), __ldg(&tw[3 * t]));
-        }
+        for (int m = 0; m < 4; ++m)
+            bfly4_dif(v[m], v[m + 4], v[m + 8], v[m + 12], true, m ? cmul(a1, w16(m)) : a1, m ? cmul(a2, w16(2 * m)) : a2,
+                      m ? cmul(a3, w16(3 * m)) : a3);
         // stage B: quarter q, butterflies (4a, 4a+1, 4a+2, 4a+3), position j
-        const int tb = j << (10 - lq);  // j * N / (4q)
-        const bool twb = lq > 0;
-        const float2 w1 = twb ? __ldg(&tw[tb]) : make_float2(1.f, 0.f);
-        const float2 w2 = twb ? __ldg(&tw[2 * tb]) : make_float2(1.f, 0.f);
-        const float2 w3 = twb ? __ldg(&tw[3 * tb]) : make_float2(1.f, 0.f);
 #pragma unroll
         for (int a = 0; a < 4; ++a) bfly4_dif(v[4 * a], v[4 * a + 1], v[4 * a + 2], v[4 * a + 3], twb, w1, w2, w3);
 #pragma unroll
@@ -188,22 +208,22 @@ __device__ void fft_dit4_inv(float2 *s, const float2 *__restrict__ tw) {
         const int q = 1 << lq;
         const int j = threadIdx.x & (q - 1);
         const int base = ((threadIdx.x >> lq) << (lq + 4)) + j;
+        const bool twb = lq > 0;
+        const int ta = j << (8 - lq);
+        const int tb = j << (10 - lq);
+        const float2 one = make_float2(1.f, 0.f);
+        const float2 a1 = twb ? __ldg(&tw[ta]) : one, a2 = twb ? __ldg(&tw[2 * ta]) : one, a3 = twb ? __ldg(&tw[3 * ta]) : one;
+        const float2 w1 = twb ? __ldg(&tw[tb]) : one, w2 = twb ? __ldg(&tw[2 * tb]) : one, w3 = twb ? __ldg(&tw[3 * tb]) : one;
         float2 v[16];
 #pragma unroll
         for (int m = 0; m < 16; ++m) v[m] = s[pidx(base + m * q)];
         // stage B first (quarter q), then stage A (quarter 4q): the mirror of the forward pass
-        const int tb = j << (10 - lq);
-        const bool twb = lq > 0;
-        const float2 w1 = twb ? __ldg(&tw[tb]) : make_float2(1.f, 0.f);
-        const float2 w2 = twb ? __ldg(&tw[2 * tb]) : make_float2(1.f, 0.f);
-        const float2 w3 = twb ? __ldg(&tw[3 * tb]) : make_float2(1.f, 0.f);
 #pragma unroll
         for (int a = 0; a < 4; ++a) bfly4_dit_inv(v[4 * a], v[4 * a + 1], v[4 * a + 2], v[4 * a + 3], twb, w1, w2, w3);
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const int t = (j + m * q) << (8 - lq);
-            bfly4_dit_inv(v[m], v[m + 4], v[m + 8], v[m + 12], true, __ldg(&tw[t]), __ldg(&tw[2 * t]), __ldg(&tw[3 * t]));
-        }
+        for (int m = 0; m < 4; ++m)
+            bfly4_dit_inv(v[m], v[m + 4], v[m + 8], v[m + 12], true, m ? cmul(a1, w16(m)) : a1, m ? cmul(a2, w16(2 * m)) : a2,
+                          m ? cmul(a3, w16(3 * m)) : a3);
 #pragma unroll
         for (int m = 0; m < 16; ++m) s[pidx(base + m * q)] = v[m];
         __syncthreads();
@@ -251,14 +271,21 @@ __global__ void __launch_bounds__(kFftThreads) fir_fwd_kernel(const float *__res
     const float *xa = x + ca * ldx;
     const float *xb = x + cb * ldx;
     const int64_t nbase = (k - 1) * kB;
-    for (int i = threadIdx.x; i < kN; i += kFftThreads) {
-        const int64_t n = nbase + i;
-        const bool ok = n >= 0 && n < T;
-        s[pidx(i)] = make_float2(ok ? xa[n] : 0.f, (ok && cb < C) ? xb[n] : 0.f);
+    {
+        float2 r[kN / kFftThreads];
+#pragma unroll
+        for (int u = 0; u < kN / kFftThreads; ++u) {
+            const int64_t n = nbase + threadIdx.x + u * kFftThreads;
+            const bool ok = n >= 0 && n < T;
+            r[u] = make_float2(ok ? __ldg(&xa[n]) : 0.f, (ok && cb < C) ? __ldg(&xb[n]) : 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kN / kFftThreads; ++u) s[pidx(threadIdx.x + u * kFftThreads)] = r[u];
     }
     __syncthreads();
     fft_dif4(s, tw);
-    for (int i = threadIdx.x; i < kN; i += kFftThreads) out[i] = s[pidx(i)];
+#pragma unroll
+    for (int u = 0; u < kN / kFftThreads; ++u) out[threadIdx.x + u * kFftThreads] = s[pidx(threadIdx.x + u * kFftThreads)];
 }
 
 // Y[pair][j] = sum_p H[p] . Z[pair][j + (P-1) - p],  j in [0, nout)
@@ -328,7 +355,13 @@ __global__ void __launch_bounds__(kFftThreads) fir_inv_kernel(const float2 *__re
     const int64_t j = blockIdx.x;
     const int64_t pair = blockIdx.y;
     const float2 *in = Y + (pair * nout + j) * kN;
-    for (int i = threadIdx.x; i < kN; i += kFftThreads) s[pidx(i)] = in[i];
+    {   // all 16 loads of a thread in flight before the first shared-memory store
+        float2 r[kN / kFftThreads];
+#pragma unroll
+        for (int u = 0; u < kN / kFftThreads; ++u) r[u] = __ldcs(&in[threadIdx.x + u * kFftThreads]);
+#pragma unroll
+        for (int u = 0; u < kN / kFftThreads; ++u) s[pidx(threadIdx.x + u * kFftThreads)] = r[u];
+    }
     __syncthreads();
     fft_dit4_inv(s, tw);
     const int64_t ca = 2 * pair, cb = 2 * pair + 1;
