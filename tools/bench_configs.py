@@ -27,6 +27,63 @@ except Exception:
     PEAK = 6650.0
 
 
+def cpu_reference(kind: str):
+    """Reference CPU path timed beside the GPU number, on a bounded slice:
+    the unmodified reference extension (oracle/_ref) for the SOS paths, the numpy restatement of
+    the reference's torch.fft overlap-save for FIR (the reference Python package cannot travel)."""
+    import time
+
+    from oracle import ref_loader
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ext = ref_loader.load_ref_ext() if ref_loader.have_ref_ext() else None
+
+    def sos_call(x32, sos_np):
+        sos_t = torch.from_numpy(np.ascontiguousarray(sos_np))
+        if ext is None:
+            return oracle.sos_cascade(x32.numpy(), sos_np)[0]
+        C, K = x32.shape[0], sos_t.shape[0]
+        z = torch.zeros(K, C, 2, dtype=torch.float64)
+        return ext.sos_forward(x32.to(torch.float64), sos_t, sos_t, z, z.clone())[0].to(torch.float32)
+
+    g = torch.Generator().manual_seed(1)
+    if kind == "cfg4":
+        x = 0.1 * torch.randn(2048, 5 * FS, generator=g)
+        fs_ = [fx.filter.LoButterworth(5000, order=4, fs=FS), fx.filter.ParametricEQ(1000, q=2.0, gain=3.0, fs=FS),
+               fx.filter.HiShelving(8000, q=0.707, gain=2.0, gain_scale="db", fs=FS)]
+        for f in fs_:
+            f.compute_coefficients()
+        sos = np.vstack([f._sos.numpy() for f in fs_])
+        sos_call(x[:, :4800], sos)
+        t0 = time.perf_counter()
+        sos_call(x, sos)
+        dt = time.perf_counter() - t0
+        return {"Gsamples_s": round(x.numel() / dt / 1e9, 3), "cores": cores, "kind": "reference" if ext else "port",
+                "sample": "2048 ch x 5 s, fused K=4 cascade (one sos_forward call)"}
+    if kind == "cfg5":
+        x = 0.1 * torch.randn(32, 10 * FS, generator=g)
+        bank = fx.filter.LogFilterBank(n_bands=32, f_min=20.0, f_max=20000.0, q=1.414, fs=FS)
+        bank.compute_coefficients()
+        t0 = time.perf_counter()
+        torch.stack([sos_call(x, f._sos.numpy()) for f in bank.filters])  # the reference's Python loop + stack
+        dt = time.perf_counter() - t0
+        return {"G_lane_samples_s": round(32 * x.numel() / dt / 1e9, 3), "cores": cores, "kind": "reference" if ext else "port",
+                "sample": "32 bands x 32 ch x 10 s (32 sos_forward calls + stack)"}
+    if kind == "cfg3":
+        rng = np.random.default_rng(7)
+        K = 65536
+        ir = rng.standard_normal(K) * np.exp(-np.arange(K) / 8000.0)
+        ir = (ir / np.sqrt((ir ** 2).sum())).astype(np.float32)
+        x = (0.1 * rng.standard_normal((1, 16, 30 * FS))).astype(np.float32)
+        t0 = time.perf_counter()
+        oracle.fft_conv1d(x, ir[::-1].copy(), padding=(K - 1, 0))
+        dt = time.perf_counter() - t0
+        return {"Gsamples_s": round(x.size / dt / 1e9, 3), "cores": 1, "kind": "port",
+                "sample": "16 ch x 30 s, numpy restatement of the reference's overlap-save (block = 5K), single thread"}
+    return None
+
+
 def timed(fn, reps=5):
     fn()
     torch.cuda.synchronize()
@@ -74,6 +131,7 @@ def cfg4():
     sos = np.vstack([f._sos.numpy() for f in fs_])
     want, _, _ = oracle.sos_cascade(x[:4, : 1 << 18].cpu().numpy(), sos)
     out["parity_rel_err"] = rel(y.cpu().numpy(), want)
+    out["cpu_baseline"] = cpu_reference("cfg4")
     return {"config": f"cfg4: fused LoButterworth|ParametricEQ|HiShelving, {C} ch x {SECONDS:g} s", **out}
 
 
@@ -110,6 +168,7 @@ def cfg5():
     y = comb(x[:2, : 1 << 17])
     want = oracle.filterbank_sum(x[:2, : 1 << 17].cpu().numpy(), np.stack([f._sos.numpy() for f in fl]))
     out["sum"]["parity_rel_err"] = rel(y.cpu().numpy(), want)
+    out["cpu_baseline"] = cpu_reference("cfg5")
     return {"config": f"cfg5: LogFilterBank(32) x 256 ch (stack) and 8 BiquadBPF + over 1024 ch (sum), {SECONDS:g} s", **out}
 
 
@@ -133,6 +192,7 @@ def cfg3():
         fk = fx.filter.FIR(b)
         ms, _ = timed(lambda: fk(x), reps=3)
         out[f"taps_{k}"] = {"ms": round(ms, 3), "Gsamples_s": round(C * T / ms / 1e6, 1)}
+    out["cpu_baseline"] = cpu_reference("cfg3")
     return {"config": f"cfg3: FIR overlap-save, 65536-tap IR, {C} ch x {SECONDS:g} s", **out}
 
 
