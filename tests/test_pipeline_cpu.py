@@ -67,15 +67,46 @@ def test_gain_splits_runs_and_laziness():
     w = fx.Wave(x, FS)
     for m in f:
         w = w | m
-    kinds = [type(m).__name__ for m in w._plan()]
-    assert kinds == ["FusedSOSCascade", "Gain", "FusedSOSCascade"]
+    import torchfx_b200.wave as wave_mod
+
+    # reference structure (wave.py:227-233): the gain breaks the IIR run
+    wave_mod.FOLD_GAIN = False
+    try:
+        kinds = [type(m).__name__ for m in w._plan()]
+        assert kinds == ["FusedSOSCascade", "Gain", "FusedSOSCascade"]
+        y_unfolded = (fx.Wave(x, FS) | f[0] | f[1] | f[2] | f[3] | f[4]).ys
+    finally:
+        wave_mod.FOLD_GAIN = True
+    # default: the gain is folded into the coefficients, one cascade of all four filters
+    plan = w._plan()
+    assert [type(m).__name__ for m in plan] == ["FusedSOSCascade"]
+    assert plan[0]._num_sections == 4 and plan[0].gain == 0.5
     assert f[0]._state_x is None  # lazy: nothing ran
     y = w.ys
+    np.testing.assert_allclose(y.numpy(), y_unfolded.numpy(), atol=2e-6)
     ref = _sequential(x, f[:2]) * 0.5
     ref = sps.sosfilt(f[4]._sos.numpy(), sps.sosfilt(f[3]._sos.numpy(), ref, axis=-1), axis=-1)
     np.testing.assert_allclose(y.numpy(), ref, atol=2e-6)
     with pytest.raises(TypeError, match="Expected nn.Module"):
         fx.Wave(x, FS) | 3
+
+
+def test_gain_folding_rules():
+    torch.manual_seed(4)
+    x = torch.randn(2, 4000)
+    lo, hi = LoButterworth(3000, order=2), HiButterworth(100, order=2)
+    # leading / trailing / dB gains fold; a clamping gain and a single-IIR run do not
+    w = fx.Wave(x, FS) | fx.Gain(2.0) | lo | fx.Gain(-6.0, gain_type="db") | hi | fx.Gain(0.25)
+    plan = w._plan()
+    assert [type(m).__name__ for m in plan] == ["FusedSOSCascade"]
+    g = 2.0 * 10 ** (-6.0 / 20) * 0.25
+    assert abs(plan[0].gain - g) < 1e-12
+    ref = _sequential(x, [lo, hi]) * g
+    np.testing.assert_allclose(w.ys.numpy(), ref, atol=2e-6)
+    w = fx.Wave(x, FS) | lo | fx.Gain(4.0, clamp=True) | hi
+    assert [type(m).__name__ for m in w._plan()] == ["LoButterworth", "Gain", "HiButterworth"]
+    w = fx.Wave(x, FS) | fx.Gain(0.5) | LoButterworth(3000, order=2)
+    assert [type(m).__name__ for m in w._plan()] == ["Gain", "LoButterworth"]
 
 
 def test_fused_construction_errors_and_from_chain():

@@ -161,6 +161,54 @@ def sos_cascade_(
     return y if y.dtype == in_dtype else y.to(in_dtype)
 
 
+def sos_cascade_host_(
+    x_host: Tensor,
+    sos_cpu: Tensor,
+    state_x: Tensor | None = None,
+    state_y: Tensor | None = None,
+    *,
+    out: Tensor | None = None,
+    device: int | str | torch.device = 0,
+    chunk: int = 0,
+    precision: str | None = None,
+) -> Tensor:
+    """HOST ``[C, T]`` float32 in, HOST float32 out, filtered on ``device`` by the library's
+    streaming driver (``tfx_sos_cascade_host_f32``): time chunks of ``chunk`` samples (0 =
+    library default) with the copy-in of chunk i+1, the kernel of chunk i and the copy-out
+    of chunk i-1 overlapped, DF1 state carried on the device between chunks.  ``state_x`` /
+    ``state_y`` are HOST ``[K, C, 2]`` float64 tensors updated in place (``None`` = zero
+    state, discarded).  Pinned buffers (``x.pin_memory()``) run at full PCIe speed.
+
+    Reference caller: the chunked file driver, src/torchfx/realtime/stream.py:160-347
+    (per-chunk ``.to(device)`` / module call / ``.cpu()``, no overlap)."""
+    lib = N.load()
+    if x_host.ndim != 2:
+        raise ValueError(f"expected [C, T], got {tuple(x_host.shape)}")
+    if x_host.is_cuda or x_host.dtype != torch.float32:
+        raise ValueError("sos_cascade_host_ takes a float32 HOST tensor (use sos_cascade_ for device tensors)")
+    sos_cpu = _canon_sos(sos_cpu)
+    K = sos_cpu.shape[0]
+    xw = _rows(x_host)
+    C, T = xw.shape
+    if out is None:
+        out = torch.empty((C, T), dtype=torch.float32, pin_memory=xw.is_pinned())
+    elif out.shape != xw.shape or out.dtype != torch.float32 or out.is_cuda or (T > 1 and out.stride(-1) != 1):
+        raise ValueError("out must be a float32 host tensor shaped like x with unit-stride rows")
+    for name, s in (("state_x", state_x), ("state_y", state_y)):
+        if s is not None and (s.dtype != torch.float64 or s.is_cuda or tuple(s.shape) != (K, C, 2) or not s.is_contiguous()):
+            raise ValueError(f"{name} must be a contiguous float64 host [K={K}, C={C}, 2] tensor")
+    if (state_x is None) != (state_y is None):
+        raise ValueError("state_x and state_y must both be given or both be None")
+    dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+    index = dev.index if dev.index is not None else (torch.cuda.current_device() if torch.cuda.is_available() else 0)
+    ldx = xw.stride(0) if C > 1 else max(T, 1)
+    ldy = out.stride(0) if C > 1 else max(T, 1)
+    N.check(lib.tfx_sos_cascade_host_f32(xw.data_ptr(), out.data_ptr(), C, T, ldx, ldy, sos_cpu.data_ptr(), K,
+                                         N.ptr(state_x), N.ptr(state_y), _PRECISIONS[precision or _default_precision],
+                                         int(chunk), index))
+    return out
+
+
 def _state_like(state: Tensor | None, shape: tuple[int, ...], device: torch.device) -> Tensor:
     """Fresh float64 state on ``device`` (zeros when ``None``), never aliasing the input:
     the reference's wrappers are functional (iir_cpu.cpp:72-73 clones)."""

@@ -18,7 +18,9 @@ from .iir import IIR
 
 
 class FusedSOSCascade(nn.Module):
-    def __init__(self, *filters: IIR | Biquad) -> None:
+    def __init__(self, *filters: IIR | Biquad, gain: float = 1.0) -> None:
+        """``gain`` (extension): a linear factor folded into the first
+        section's b-coefficients, i.e. ``gain * H(z)`` at no extra pass over the signal."""
         super().__init__()
         if not filters:
             raise ValueError("FusedSOSCascade requires at least one IIR filter")
@@ -40,6 +42,10 @@ class FusedSOSCascade(nn.Module):
                 elif f.fs != fs:
                     raise ValueError(f"Cannot fuse filters with different sample rates: {fs} vs {f.fs}")
         self._sos: Tensor = torch.cat(rows, dim=0).to(dtype=torch.float64, device="cpu")
+        self.gain = float(gain)
+        if self.gain != 1.0:
+            self._sos = self._sos.clone()
+            self._sos[0, :3] *= self.gain
         self._num_sections: int = self._sos.shape[0]
         self.fs: int | None = fs
         self._sos_device_cache: Tensor | None = None

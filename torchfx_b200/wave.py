@@ -3,7 +3,9 @@
 Reference: src/torchfx/wave.py -- constructor/ys/to (:150-300), ``_materialize`` with the
 IIR-run fuser (:207-239), ``_deferred`` (:241-257), ``__or__`` / fs propagation
 (:578-703), ``merge`` / ``get_channel`` / ``duration`` (:705-900).  File I/O
-(``from_file`` / ``save``, soundfile) is out of scope.
+(``from_file`` :406-470, ``save`` :472-576) reads and writes WAV through the package's own
+RIFF codec (``_wavio``; soundfile is not installed here) and delegates other containers to
+``soundfile`` when it is importable.
 """
 from __future__ import annotations
 
@@ -16,6 +18,10 @@ from torch import Tensor, nn
 from .effect import FX
 from .filter._base import AbstractFilter
 from .typing import Device
+
+
+# Fold non-clamping Gain steps into the adjacent fused IIR run (see Wave._plan).
+FOLD_GAIN = True
 
 
 class Wave:
@@ -42,7 +48,15 @@ class Wave:
 
     def _plan(self) -> list[nn.Module]:
         """Group consecutive IIR/Biquad steps; a run of >= 2 becomes ONE FusedSOSCascade
-        (fresh instance => zero state per materialisation, reference wave.py:216-233)."""
+        (fresh instance => zero state per materialisation, reference wave.py:216-233).
+
+        With ``FOLD_GAIN`` (module switch, default on) a non-clamping ``Gain`` next to or
+        between IIR steps does not break the run: scaling is linear, so
+        its factor is multiplied into the b-coefficients of the fused cascade and the
+        separate 8 B/sample pass of reference wave.py:227-233 disappears.  A run that holds
+        a single IIR keeps the reference's behaviour (the module itself runs and keeps its
+        own state), so gains around it stay separate steps."""
+        from .effect import Gain
         from .filter.biquad import Biquad
         from .filter.fused import FusedSOSCascade
         from .filter.iir import IIR
@@ -51,14 +65,22 @@ class Wave:
         run: list[nn.Module] = []
 
         def close_run() -> None:
-            if len(run) >= 2:
-                plan.append(FusedSOSCascade(*run))
+            filters = [m for m in run if isinstance(m, (IIR, Biquad))]
+            if len(filters) >= 2:
+                # gains at the tail of the run that follow the last filter still fold
+                g = 1.0
+                for m in run:
+                    if isinstance(m, Gain):
+                        g *= m.linear_gain()
+                plan.append(FusedSOSCascade(*filters, gain=g))
             else:
                 plan.extend(run)
             run.clear()
 
         for step in self._pipeline:
             if isinstance(step, (IIR, Biquad)):
+                run.append(step)
+            elif FOLD_GAIN and isinstance(step, Gain) and not step.clamp:
                 run.append(step)
             else:
                 close_run()
@@ -120,6 +142,64 @@ class Wave:
             f.fs = self.fs
         if isinstance(f, AbstractFilter) and not f._has_computed_coeff:
             f.compute_coefficients()
+
+    # ---- file I/O (reference wave.py:406-576) ------------------------------------------------
+    @classmethod
+    def from_file(cls, path, frame_offset: int = 0, num_frames: int = -1) -> "Wave":
+        from . import _wavio
+
+        stop = None if num_frames == -1 else frame_offset + num_frames
+        if _wavio.is_wav_path(path):
+            meta = _wavio.info(path)
+            data_np, fs = _wavio.read(path, start=frame_offset, stop=stop, meta=meta)
+            metadata = {"num_frames": meta.frames, "num_channels": meta.channels, "subtype": meta.subtype,
+                        "format": meta.format}
+        else:
+            try:
+                import soundfile as _sf
+            except ImportError as e:  # pragma: no cover - depends on the image
+                raise ImportError(f"reading {path} needs the 'soundfile' package (only WAV is built in)") from e
+            data_np, fs = _sf.read(str(path), start=frame_offset, stop=stop, dtype="float32", always_2d=True)
+            i = _sf.info(str(path))
+            metadata = {"num_frames": i.frames, "num_channels": i.channels, "subtype": i.subtype, "format": i.format}
+        return cls(torch.from_numpy(data_np.T.copy()), fs, metadata=metadata)
+
+    def save(self, path, format: str | None = None, encoding: str | None = None,  # noqa: A002
+             bits_per_sample: int | None = None) -> None:
+        import os
+
+        from . import _wavio
+
+        parent = os.path.dirname(str(path))
+        if parent:
+            os.makedirs(parent, exist_ok=True)
+        audio = self.ys.cpu()
+        # encoding / bits_per_sample -> libsndfile subtype, as reference wave.py:548-565
+        subtype: str | None = None
+        if encoding is not None and bits_per_sample is not None:
+            if encoding == "PCM_S":
+                subtype = f"PCM_{bits_per_sample}"
+            elif encoding == "PCM_U":
+                subtype = "PCM_U8" if bits_per_sample == 8 else f"PCM_{bits_per_sample}"
+            elif encoding == "PCM_F":
+                subtype = "FLOAT" if bits_per_sample == 32 else "DOUBLE"
+            else:
+                subtype = f"{encoding}{bits_per_sample}"
+        elif bits_per_sample is not None:
+            subtype = f"PCM_{bits_per_sample}"
+        elif encoding == "PCM_F":
+            subtype = "FLOAT"
+        frames = audio.numpy().T if audio.ndim == 2 else audio.numpy()
+        if _wavio.is_wav_path(path, format):
+            _wavio.write(path, frames, self.fs, subtype)
+            return
+        try:
+            import soundfile as _sf
+        except ImportError as e:  # pragma: no cover - depends on the image
+            raise ImportError(f"writing {path} needs the 'soundfile' package (only WAV is built in)") from e
+        ext = os.path.splitext(str(path))[1].lower()
+        fmt = format or {".flac": "FLAC", ".ogg": "OGG"}.get(ext, "WAV")
+        _sf.write(str(path), frames, self.fs, format=fmt, subtype=subtype)
 
     # ---- small accessors ------------------------------------------------------------------
     def __len__(self) -> int:
