@@ -9,7 +9,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torchfx_b200 as fx  # noqa: E402
-from torchfx_b200.dist import ChannelSharded, all_gather_channels, shard_bounds, shard_channels  # noqa: E402
+from torchfx_b200.dist import ChannelSharded, all_gather_channels, filter_and_gather, shard_bounds, shard_channels  # noqa: E402
 
 
 def main():
@@ -33,6 +33,15 @@ def main():
         g = ChannelSharded(fx.filter.LoButterworth(3000, order=6, fs=48000), gather=True)
         y = torch.cat([g(x[:, :2500]), g(x[:, 2500:])], dim=1)
         np.testing.assert_allclose(y.numpy(), ref, atol=1e-10)
+        # chunked gather (each time chunk gathered as soon as it is filtered; overlapped on GPUs)
+        gc = ChannelSharded(fx.filter.LoButterworth(3000, order=6, fs=48000), gather=True, gather_chunk=1024)
+        np.testing.assert_allclose(gc(x).numpy(), ref, atol=1e-10)
+    try:
+        filter_and_gather(fx.filter.FIR([1.0, 0.5]), torch.randn(2, 100), 4, 32)
+    except TypeError as e:
+        assert "does not carry state" in str(e)
+    else:
+        raise AssertionError("filter_and_gather accepted a stateless module")
     # filterbank lanes: shard channels, gather per band
     x = torch.randn(4, 3000)
     bank = fx.filter.LogFilterBank(n_bands=4, f_min=200.0, f_max=4000.0, fs=48000)

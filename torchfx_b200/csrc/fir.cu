@@ -255,11 +255,13 @@ __global__ void __launch_bounds__(kFftThreads) fir_taps_fft_kernel(const float *
 }
 
 // Z[pair][row] = DIF-FFT(x_a[(k-1)B : (k+1)B] + i x_b[...]),  k = k_first + row (k < 0 -> zeros)
+// Rows [row0, row0 + gridDim.x) of the slab are computed; rows below row0 hold the previous slab's
+// last P-1 spectra (copied there by the host loop), nrows is the row pitch of Z per pair.
 __global__ void __launch_bounds__(kFftThreads) fir_fwd_kernel(const float *__restrict__ x, int64_t C, int64_t T, int64_t ldx,
-                                                             int64_t k_first, int64_t nrows, float2 *__restrict__ Z,
-                                                             const float2 *__restrict__ tw) {
+                                                             int64_t k_first, int64_t nrows, int64_t row0,
+                                                             float2 *__restrict__ Z, const float2 *__restrict__ tw) {
     __shared__ float2 s[kPadN];
-    const int64_t row = blockIdx.x;
+    const int64_t row = row0 + blockIdx.x;
     const int64_t pair = blockIdx.y;
     const int64_t k = k_first + row;
     float2 *out = Z + (pair * nrows + row) * kN;
@@ -464,12 +466,22 @@ int tfx_fir_f32(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int
     TFX_CHECK_LAUNCH("fir_taps_fft_kernel");
     const size_t mac_smem = sizeof(float2) * (kMacRows + kMacPc) * kMacBins;
     TFX_ENSURE_SMEM(fir_mac_kernel, static_cast<int>(mac_smem));
+    const size_t row_bytes = sizeof(float2) * kN;
     for (int64_t k0 = 0; k0 < L.nblk; k0 += L.slab) {
         const int64_t nout = std::min<int64_t>(L.slab, L.nblk - k0);
-        const int64_t nrows = nout + L.P - 1;
+        const int64_t nrows = L.nrows;  // row pitch of Z per pair, the same for every slab
         const int64_t k_first = k0 - (L.P - 1);
-        fir_fwd_kernel<<<dim3(static_cast<unsigned>(nrows), static_cast<unsigned>(L.npairs)), kFftThreads, 0, stream>>>(
-            x, C, T, ldx, k_first, nrows, Z, tw);
+        // The P-1 history spectra of this slab are the last P-1 rows of the previous one: move them
+        // to the front (device-to-device, ~1 % of a slab's traffic) instead of transforming the
+        // same input blocks again; the first slab's history (k < 0) is written as zeros by the kernel.
+        int64_t row0 = 0;
+        if (k0 > 0 && L.P > 1) {
+            row0 = L.P - 1;
+            TFX_CUDA_TRY(cudaMemcpy2DAsync(Z, nrows * row_bytes, Z + L.slab * kN, nrows * row_bytes, row0 * row_bytes,
+                                           static_cast<size_t>(L.npairs), cudaMemcpyDeviceToDevice, stream));
+        }
+        fir_fwd_kernel<<<dim3(static_cast<unsigned>(nout + L.P - 1 - row0), static_cast<unsigned>(L.npairs)), kFftThreads, 0,
+                         stream>>>(x, C, T, ldx, k_first, nrows, row0, Z, tw);
         TFX_CHECK_LAUNCH("fir_fwd_kernel");
         fir_mac_kernel<<<dim3(kN / kMacBins, static_cast<unsigned>((nout + kMacBlocks - 1) / kMacBlocks),
                               static_cast<unsigned>(L.npairs)),

@@ -64,20 +64,88 @@ def all_gather_channels(y_local: Tensor, num_channels: int, group=None, out: Ten
     return out
 
 
+def _carries_state(module: nn.Module) -> bool:
+    """True for the SOS filters whose DF1 state makes chunk-by-chunk calls equal one call."""
+    from .filter.biquad import Biquad
+    from .filter.fused import FusedSOSCascade
+    from .filter.iir import IIR
+
+    return isinstance(module, (IIR, Biquad, FusedSOSCascade))
+
+
+_comm_streams: dict[int, "torch.cuda.Stream"] = {}
+
+
+def filter_and_gather(module: nn.Module, x_local: Tensor, num_channels: int, chunk: int, group=None,
+                      out: Tensor | None = None) -> Tensor:
+    """Filter this rank's ``[C_r, T]`` block in time chunks and all-gather every chunk while the
+    next one is being filtered (the gather moves P x the kernel's bytes over NVLink,
+    so it is hidden behind -- or rather hides -- the compute instead of following it).
+
+    ``module`` must be a state-carrying SOS filter (IIR / Biquad / FusedSOSCascade): consecutive
+    calls on consecutive chunks are then identical to one call (reference filter/iir.py:135-144).
+    Chunk i is gathered on a side stream into a contiguous ``[P*C_r, n]`` staging buffer and
+    copied into ``out[:, t0:t1]`` there; the compute stream only waits at the end.
+    """
+    if not _carries_state(module):
+        raise TypeError(f"{type(module).__name__} does not carry state across calls; chunked gather needs an SOS filter")
+    if chunk <= 0:
+        raise ValueError(f"chunk must be positive, got {chunk}")
+    world, _ = _world(group)
+    C_r, T = x_local.shape
+    if out is None:
+        out = torch.empty((num_channels, T), dtype=x_local.dtype, device=x_local.device)
+    if world == 1 or num_channels % world != 0 or num_channels != world * C_r:
+        return all_gather_channels(module(x_local), num_channels, group, out)
+    cuda = x_local.is_cuda
+    if cuda:
+        idx = x_local.device.index if x_local.device.index is not None else torch.cuda.current_device()
+        comm = _comm_streams.get(idx)
+        if comm is None:
+            comm = _comm_streams[idx] = torch.cuda.Stream(device=x_local.device)
+        compute = torch.cuda.current_stream(x_local.device)
+        comm.wait_stream(compute)  # `out` and the staging buffers are allocated on the compute stream
+    stage = [torch.empty(num_channels * min(chunk, T), dtype=x_local.dtype, device=x_local.device) for _ in range(2)]
+    for i, t0 in enumerate(range(0, T, chunk)):
+        n = min(chunk, T - t0)
+        y = module(x_local[:, t0 : t0 + n])
+        if not y.is_contiguous():
+            y = y.contiguous()
+        buf = stage[i % 2][: num_channels * n].view(num_channels, n)
+        if cuda:
+            comm.wait_stream(compute)
+            with torch.cuda.stream(comm):
+                dist.all_gather_into_tensor(buf, y, group=group)
+                out[:, t0 : t0 + n].copy_(buf)
+            y.record_stream(comm)
+        else:
+            dist.all_gather_into_tensor(buf, y, group=group)
+            out[:, t0 : t0 + n].copy_(buf)
+    if cuda:
+        compute.wait_stream(comm)
+        for b in stage:
+            b.record_stream(comm)
+    return out
+
+
 class ChannelSharded(nn.Module):
     """Run ``module`` on this rank's channel block of a ``[C, T]`` input.
 
     ``gather=False`` (default) returns the local block -- no collective on the data path.
-    ``gather=True`` all-gathers the blocks so every rank returns the full ``[C, T]``.
+    ``gather=True`` all-gathers the blocks so every rank returns the full ``[C, T]``; with
+    ``gather_chunk`` (samples) and a state-carrying SOS filter the gather of each time chunk
+    overlaps the filtering of the next one (``filter_and_gather``).
     The wrapped filter's state is rank-local (``[K, C/P, 2]``), coefficients are replicated.
     """
 
-    def __init__(self, module: nn.Module, group=None, gather: bool = False, input_is_sharded: bool = False) -> None:
+    def __init__(self, module: nn.Module, group=None, gather: bool = False, input_is_sharded: bool = False,
+                 gather_chunk: int | None = None) -> None:
         super().__init__()
         self.module = module
         self.group = group
         self.gather = gather
         self.input_is_sharded = input_is_sharded
+        self.gather_chunk = gather_chunk
 
     def forward(self, x: Tensor, num_channels: int | None = None) -> Tensor:
         if self.input_is_sharded:
@@ -88,6 +156,8 @@ class ChannelSharded(nn.Module):
         else:
             total = x.shape[-2]
             local = shard_channels(x, self.group)
+        if self.gather and self.gather_chunk and local.ndim == 2 and _carries_state(self.module):
+            return filter_and_gather(self.module, local, int(total), self.gather_chunk, self.group)
         y = self.module(local)
         if not self.gather:
             return y
