@@ -67,9 +67,11 @@ def test_tap_counts_both_algorithms(algo, K):
     assert rel_to_max(y.cpu().numpy(), want) < TOL
 
 
-@pytest.mark.parametrize("K,T", [(2048, 5000), (2049, 5000), (5000, 3000), (4096, 4096), (12345, 40000), (300, 100)])
+@pytest.mark.parametrize("K,T", [(2048, 5000), (2049, 5000), (5000, 3000), (4096, 4096), (12345, 40000), (300, 100),
+                                 (20000, 30000), (70000, 150000), (131072, 140000)])
 def test_partition_edges(K, T):
-    """K around the 2048-tap partition, K > T, T around the 2048-sample block."""
+    """K around the 2048-tap partition, K > T, T around the 2048-sample block; partition counts
+    that are not a multiple of the 32-partition chunk (10, 35) and two full chunks (64)."""
     rng = np.random.default_rng(K + T)
     x = rng.standard_normal((2, T)).astype(np.float32)
     b = (rng.standard_normal(K) * np.exp(-np.arange(K) / (K / 4))).astype(np.float32)
@@ -91,15 +93,16 @@ def test_cfg3_reverb_ir_65536_taps():
     assert rel_to_max(y, want) < TOL
 
 
-def test_many_channels_multiple_slabs_linearity():
-    """256 channels x 600k samples: the spectra workspace is processed in several time slabs.
+@pytest.mark.parametrize("K", [5000, 40000])
+def test_many_channels_multiple_slabs_linearity(K):
+    """256 channels x 600k samples: the spectra workspace is processed in several time slabs and the
+    spectra ring wraps (3 and 20 partitions of history carried from slab to slab).
     Checked by linearity + a 4-channel oracle comparison (the full oracle would take minutes)."""
     g = torch.Generator(device=DEV).manual_seed(5)
     x1 = 0.1 * torch.randn(256, 600_000, device=DEV, generator=g)
     x2 = 0.1 * torch.randn(256, 600_000, device=DEV, generator=g)
     rng = np.random.default_rng(11)
-    K = 5000
-    b = (rng.standard_normal(K) * np.exp(-np.arange(K) / 700.0)).astype(np.float32)
+    b = (rng.standard_normal(K) * np.exp(-np.arange(K) / (K / 7.0))).astype(np.float32)
     bt = torch.from_numpy(b)
     y1 = fir_causal(x1, bt)
     y2 = fir_causal(x2, bt)

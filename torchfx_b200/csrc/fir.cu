@@ -45,7 +45,6 @@ constexpr int kMacBins = 64;          // bins per MAC CTA
 constexpr int kMacBlocks = 64;        // output blocks per MAC CTA
 constexpr int kMacPc = 32;            // partitions per shared-memory chunk
 constexpr int kMacRows = kMacBlocks + kMacPc - 1;  // 95 spectra rows staged per chunk
-constexpr size_t kTwBytes = sizeof(float2) * kN;
 
 // ------------------------------------------------------------------------------------------
 // DIRECT
@@ -169,212 +168,361 @@ __device__ __forceinline__ float2 w16(int k) {
     }
 }
 
-// forward, decimation in frequency: natural order in, base-4 digit-reversed order out.
-// Pass with stride q (= 256, 16, 1) fuses the radix-4 stages of quarter 4q and q.
-__device__ void fft_dif4(float2 *s, const float2 *__restrict__ tw) {
-#pragma unroll 1
-    for (int lq = 8; lq >= 0; lq -= 4) {
-        const int q = 1 << lq;
-        const int j = threadIdx.x & (q - 1);
-        const int base = ((threadIdx.x >> lq) << (lq + 4)) + j;
-        // twiddle loads first (global, L1/L2): their latency overlaps the shared-memory loads
-        const bool twb = lq > 0;
-        const int ta = j << (8 - lq);   // j * N / (16q)
-        const int tb = j << (10 - lq);  // j * N / (4q)
-        const float2 one = make_float2(1.f, 0.f);
-        const float2 a1 = twb ? __ldg(&tw[ta]) : one, a2 = twb ? __ldg(&tw[2 * ta]) : one, a3 = twb ? __ldg(&tw[3 * ta]) : one;
-        const float2 w1 = twb ? __ldg(&tw[tb]) : one, w2 = twb ? __ldg(&tw[2 * tb]) : one, w3 = twb ? __ldg(&tw[3 * tb]) : one;
-        float2 v[16];
-#pragma unroll
-        for (int m = 0; m < 16; ++m) v[m] = s[pidx(base + m * q)];
-        // stage A: quarter 4q, butterflies (m, m+4, m+8, m+12), position jj = j + m*q
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-            bfly4_dif(v[m], v[m + 4], v[m + 8], v[m + 12], true, m ? cmul(a1, w16(m)) : a1, m ? cmul(a2, w16(2 * m)) : a2,
-                      m ? cmul(a3, w16(3 * m)) : a3);
-        // stage B: quarter q, butterflies (4a, 4a+1, 4a+2, 4a+3), position j
-#pragma unroll
-        for (int a = 0; a < 4; ++a) bfly4_dif(v[4 * a], v[4 * a + 1], v[4 * a + 2], v[4 * a + 3], twb, w1, w2, w3);
-#pragma unroll
-        for (int m = 0; m < 16; ++m) s[pidx(base + m * q)] = v[m];
-        __syncthreads();
+// Twiddles of one thread for one pass, W = exp(-2*pi*i/N), j = the thread's position inside its
+// 16q-point group:  a_r = W^{r * j * N/(16q)},  w_r = W^{r * j * N/(4q)},  r = 1..3.
+// They are tabulated per (pass, j) as six consecutive float2 (48 bytes, three 16-byte loads that
+// neighbouring lanes coalesce) -- the first version gathered them from one N-entry table with
+// strides up to 96 bytes, and those gathers cost as many L1 cycles as the shared-memory traffic.
+struct Tw6 {
+    float2 a1, a2, a3, w1, w2, w3;
+};
+constexpr int kTwEntries = 256 + 16;  // pass q = 256 (j < 256) then pass q = 16 (j < 16)
+constexpr size_t kTwBytes = sizeof(Tw6) * kTwEntries;
+template <int LQ>
+__device__ __forceinline__ Tw6 load_tw(const float4 *__restrict__ tab, int j) {
+    Tw6 t;
+    if constexpr (LQ == 0) {
+        t.a1 = t.a2 = t.a3 = t.w1 = t.w2 = t.w3 = make_float2(1.f, 0.f);
+    } else {
+        const float4 *e = tab + 3 * ((LQ == 8 ? 0 : 256) + j);
+        const float4 u0 = __ldg(e), u1 = __ldg(e + 1), u2 = __ldg(e + 2);
+        t.a1 = make_float2(u0.x, u0.y);
+        t.a2 = make_float2(u0.z, u0.w);
+        t.a3 = make_float2(u1.x, u1.y);
+        t.w1 = make_float2(u1.z, u1.w);
+        t.w2 = make_float2(u2.x, u2.y);
+        t.w3 = make_float2(u2.z, u2.w);
     }
+    return t;
 }
 
-// inverse (unscaled), decimation in time: digit-reversed order in, natural order out
-__device__ void fft_dit4_inv(float2 *s, const float2 *__restrict__ tw) {
-#pragma unroll 1
-    for (int lq = 0; lq <= 8; lq += 4) {
-        const int q = 1 << lq;
-        const int j = threadIdx.x & (q - 1);
-        const int base = ((threadIdx.x >> lq) << (lq + 4)) + j;
-        const bool twb = lq > 0;
-        const int ta = j << (8 - lq);
-        const int tb = j << (10 - lq);
-        const float2 one = make_float2(1.f, 0.f);
-        const float2 a1 = twb ? __ldg(&tw[ta]) : one, a2 = twb ? __ldg(&tw[2 * ta]) : one, a3 = twb ? __ldg(&tw[3 * ta]) : one;
-        const float2 w1 = twb ? __ldg(&tw[tb]) : one, w2 = twb ? __ldg(&tw[2 * tb]) : one, w3 = twb ? __ldg(&tw[3 * tb]) : one;
-        float2 v[16];
+// One radix-16 step on 16 registers (two fused radix-4 stages).  Forward = decimation in frequency
+// (stage A on stride 4q, then stage B on stride q); inverse = the mirror image with conjugate twiddles.
+template <int LQ>
+__device__ __forceinline__ void radix16_dif(float2 (&v)[16], const Tw6 &t) {
 #pragma unroll
-        for (int m = 0; m < 16; ++m) v[m] = s[pidx(base + m * q)];
-        // stage B first (quarter q), then stage A (quarter 4q): the mirror of the forward pass
+    for (int m = 0; m < 4; ++m)
+        bfly4_dif(v[m], v[m + 4], v[m + 8], v[m + 12], true, m ? cmul(t.a1, w16(m)) : t.a1, m ? cmul(t.a2, w16(2 * m)) : t.a2,
+                  m ? cmul(t.a3, w16(3 * m)) : t.a3);
 #pragma unroll
-        for (int a = 0; a < 4; ++a) bfly4_dit_inv(v[4 * a], v[4 * a + 1], v[4 * a + 2], v[4 * a + 3], twb, w1, w2, w3);
+    for (int a = 0; a < 4; ++a) bfly4_dif(v[4 * a], v[4 * a + 1], v[4 * a + 2], v[4 * a + 3], LQ > 0, t.w1, t.w2, t.w3);
+}
+template <int LQ>
+__device__ __forceinline__ void radix16_dit_inv(float2 (&v)[16], const Tw6 &t) {
 #pragma unroll
-        for (int m = 0; m < 4; ++m)
-            bfly4_dit_inv(v[m], v[m + 4], v[m + 8], v[m + 12], true, m ? cmul(a1, w16(m)) : a1, m ? cmul(a2, w16(2 * m)) : a2,
-                          m ? cmul(a3, w16(3 * m)) : a3);
+    for (int a = 0; a < 4; ++a) bfly4_dit_inv(v[4 * a], v[4 * a + 1], v[4 * a + 2], v[4 * a + 3], LQ > 0, t.w1, t.w2, t.w3);
 #pragma unroll
-        for (int m = 0; m < 16; ++m) s[pidx(base + m * q)] = v[m];
-        __syncthreads();
-    }
+    for (int m = 0; m < 4; ++m)
+        bfly4_dit_inv(v[m], v[m + 4], v[m + 8], v[m + 12], true, m ? cmul(t.a1, w16(m)) : t.a1, m ? cmul(t.a2, w16(2 * m)) : t.a2,
+                      m ? cmul(t.a3, w16(3 * m)) : t.a3);
 }
 
-__global__ void fir_twiddle_kernel(float2 *tw) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < kN) {
-        double sn, cs;
-        sincospi(-2.0 * t / kN, &sn, &cs);
-        tw[t] = make_float2(static_cast<float>(cs), static_cast<float>(sn));
-    }
-}
-
-// H[p] = DIF-FFT(taps[pB:(p+1)B] zero-padded to N), one CTA per partition
-__global__ void __launch_bounds__(kFftThreads) fir_taps_fft_kernel(const float *__restrict__ taps, int64_t K, float2 *__restrict__ H,
-                                                                  const float2 *__restrict__ tw) {
-    __shared__ float2 s[kPadN];
-    const int64_t p = blockIdx.x;
-    for (int i = threadIdx.x; i < kN; i += kFftThreads) {
-        const int64_t j = p * kB + i;
-        s[pidx(i)] = make_float2((i < kB && j < K) ? taps[j] : 0.f, 0.f);
+// The 4096-point transform is three radix-16 passes with strides q = 256, 16, 1 (forward) or 1, 16,
+// 256 (inverse), 256 threads, one radix-16 per thread per pass.  Only the MIDDLE pass lives entirely
+// in shared memory: the stride-256 pass reads (forward) or writes (inverse) element j + 256 m from
+// thread j -- coalesced straight from / to global memory -- and the stride-1 pass hands thread t the
+// 16 consecutive points 16 t + m, which are stored to global memory TRANSPOSED, at m * 256 + t
+// (again coalesced).  The spectrum order is therefore "digit-reversed, then transposed"; spectra are
+// only ever multiplied point-wise with spectra in the same order, so the order never has to be undone.
+// Shared-memory traffic per transform: 2 writes + 2 reads of the 32 KB tile instead of 4 + 4.
+__device__ __forceinline__ void fft_fwd_tail(float2 (&v)[16], float2 *s, const float4 *__restrict__ tab,
+                                             float2 *__restrict__ out) {
+    const int tid = threadIdx.x;
+    // pass q = 256 (registers were filled by the caller with elements tid + 256 m)
+    radix16_dif<8>(v, load_tw<8>(tab, tid));
+#pragma unroll
+    for (int m = 0; m < 16; ++m) s[pidx(tid + 256 * m)] = v[m];
+    __syncthreads();
+    {   // pass q = 16
+        const int j = tid & 15, base = ((tid >> 4) << 8) + j;
+        const Tw6 t = load_tw<4>(tab, j);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m] = s[pidx(base + 16 * m)];
+        radix16_dif<4>(v, t);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) s[pidx(base + 16 * m)] = v[m];
     }
     __syncthreads();
-    fft_dif4(s, tw);
-    float2 *out = H + p * kN;
-    for (int i = threadIdx.x; i < kN; i += kFftThreads) out[i] = s[pidx(i)];
+    // pass q = 1
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = s[pidx(16 * tid + m)];
+    radix16_dif<0>(v, load_tw<0>(tab, 0));
+#pragma unroll
+    for (int m = 0; m < 16; ++m) out[m * 256 + tid] = v[m];
 }
 
-// Z[pair][row] = DIF-FFT(x_a[(k-1)B : (k+1)B] + i x_b[...]),  k = k_first + row (k < 0 -> zeros)
-// Rows [row0, row0 + gridDim.x) of the slab are computed; rows below row0 hold the previous slab's
-// last P-1 spectra (copied there by the host loop), nrows is the row pitch of Z per pair.
+// inverse (unscaled): `in` in the forward transform's output order, result element tid + 256 m in v[m]
+__device__ __forceinline__ void fft_inv(float2 (&v)[16], float2 *s, const float4 *__restrict__ tab,
+                                        const float2 *__restrict__ in) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = __ldcs(&in[m * 256 + tid]);
+    radix16_dit_inv<0>(v, load_tw<0>(tab, 0));
+#pragma unroll
+    for (int m = 0; m < 16; ++m) s[pidx(16 * tid + m)] = v[m];
+    __syncthreads();
+    {
+        const int j = tid & 15, base = ((tid >> 4) << 8) + j;
+        const Tw6 t = load_tw<4>(tab, j);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m] = s[pidx(base + 16 * m)];
+        radix16_dit_inv<4>(v, t);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) s[pidx(base + 16 * m)] = v[m];
+    }
+    __syncthreads();
+    const Tw6 t = load_tw<8>(tab, tid);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = s[pidx(tid + 256 * m)];
+    radix16_dit_inv<8>(v, t);
+}
+
+__global__ void fir_twiddle_kernel(float2 *tab) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;  // entry: pass q = 256 for e < 256, else q = 16
+    if (e < kTwEntries) {
+        const int ta = e < 256 ? e : (e - 256) << 4;  // j * N / (16 q)
+        for (int r = 0; r < 6; ++r) {
+            const int k = (r < 3 ? (r + 1) : 4 * (r - 2)) * ta;
+            double sn, cs;
+            sincospi(-2.0 * k / kN, &sn, &cs);
+            tab[6 * e + r] = make_float2(static_cast<float>(cs), static_cast<float>(sn));
+        }
+    }
+}
+
+// H[p] = FFT(taps[pB:(p+1)B] zero-padded to N), one CTA per partition
+__global__ void __launch_bounds__(kFftThreads) fir_taps_fft_kernel(const float *__restrict__ taps, int64_t K, float2 *__restrict__ H,
+                                                                  const float4 *__restrict__ tab) {
+    __shared__ float2 s[kPadN];
+    const int64_t p = blockIdx.x;
+    float2 v[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const int i = threadIdx.x + 256 * m;
+        const int64_t j = p * kB + i;
+        v[m] = make_float2((i < kB && j < K) ? __ldg(&taps[j]) : 0.f, 0.f);
+    }
+    fft_fwd_tail(v, s, tab, H + p * kN);
+}
+
+// Z is a ring of `nrows` spectra per pair: slab row r (block k = k_first + r) lives at ring slot
+// (ring0 + r) mod nrows, so the P-1 history spectra a slab needs are simply still there from the
+// previous slab.  Rows [row0, row0 + gridDim.x) are computed here.
+__device__ __forceinline__ int64_t ring_slot(int64_t ring0, int64_t row, int64_t nrows) {
+    const int64_t r = ring0 + row;
+    return r >= nrows ? r - nrows : r;
+}
+// Z[pair][row] = FFT(x_a[(k-1)B : (k+1)B] + i x_b[...]),  k = k_first + row (k < 0 -> zeros)
 __global__ void __launch_bounds__(kFftThreads) fir_fwd_kernel(const float *__restrict__ x, int64_t C, int64_t T, int64_t ldx,
-                                                             int64_t k_first, int64_t nrows, int64_t row0,
-                                                             float2 *__restrict__ Z, const float2 *__restrict__ tw) {
+                                                             int64_t k_first, int64_t nrows, int64_t row0, int64_t ring0,
+                                                             float2 *__restrict__ Z, const float4 *__restrict__ tab) {
     __shared__ float2 s[kPadN];
     const int64_t row = row0 + blockIdx.x;
     const int64_t pair = blockIdx.y;
     const int64_t k = k_first + row;
-    float2 *out = Z + (pair * nrows + row) * kN;
+    float2 *out = Z + (pair * nrows + ring_slot(ring0, row, nrows)) * kN;
     if (k < 0) {  // block before the start of the signal: all-zero spectrum
         for (int i = threadIdx.x; i < kN; i += kFftThreads) out[i] = make_float2(0.f, 0.f);
         return;
     }
     const int64_t ca = 2 * pair, cb = 2 * pair + 1;
     const float *xa = x + ca * ldx;
-    const float *xb = x + cb * ldx;
-    const int64_t nbase = (k - 1) * kB;
-    {
-        float2 r[kN / kFftThreads];
+    const float *xb = x + (cb < C ? cb : ca) * ldx;
+    const bool has_b = cb < C;
+    const int64_t nbase = (k - 1) * kB + threadIdx.x;
+    float2 v[16];
+    if (nbase >= 0 && nbase + 256 * 15 < T) {  // whole block inside the signal (block-uniform up to 255 samples)
 #pragma unroll
-        for (int u = 0; u < kN / kFftThreads; ++u) {
-            const int64_t n = nbase + threadIdx.x + u * kFftThreads;
+        for (int m = 0; m < 16; ++m) v[m] = make_float2(__ldg(&xa[nbase + 256 * m]), __ldg(&xb[nbase + 256 * m]));
+    } else {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int64_t n = nbase + 256 * m;
             const bool ok = n >= 0 && n < T;
-            r[u] = make_float2(ok ? __ldg(&xa[n]) : 0.f, (ok && cb < C) ? __ldg(&xb[n]) : 0.f);
+            v[m] = make_float2(ok ? __ldg(&xa[n]) : 0.f, ok ? __ldg(&xb[n]) : 0.f);
         }
-#pragma unroll
-        for (int u = 0; u < kN / kFftThreads; ++u) s[pidx(threadIdx.x + u * kFftThreads)] = r[u];
     }
-    __syncthreads();
-    fft_dif4(s, tw);
+    if (!has_b) {
 #pragma unroll
-    for (int u = 0; u < kN / kFftThreads; ++u) out[threadIdx.x + u * kFftThreads] = s[pidx(threadIdx.x + u * kFftThreads)];
+        for (int m = 0; m < 16; ++m) v[m].y = 0.f;
+    }
+    fft_fwd_tail(v, s, tab, out);
+}
+
+// 16-byte cp.async that writes zeros instead when !valid (src-size 0: nothing is read).
+__device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gmem_src, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+                 "r"(valid ? 16 : 0)
+                 : "memory");
 }
 
 // Y[pair][j] = sum_p H[p] . Z[pair][j + (P-1) - p],  j in [0, nout)
-__global__ void __launch_bounds__(512) fir_mac_kernel(const float2 *__restrict__ Z, const float2 *__restrict__ H,
-                                                     float2 *__restrict__ Y, int P, int64_t nrows, int64_t nout) {
+//
+// Persistent CTAs (one per SM, 512 threads) walk the (pair, 64-block, 64-bin) tiles; a tile with
+// P > 32 partitions is a run of 32-partition work items that accumulate in registers.  The
+// [95 x 64] spectra rows and [32 x 64] taps of item i+1 are fetched with cp.async into the other
+// half of a double buffer while item i is multiplied, so the FMA pipe never waits on a staging phase
+// (the first version loaded, synchronised and then computed with two CTAs per SM: 39 % FMA
+// utilisation, `long_scoreboard` the dominant stall).
+// Inner loop: each thread owns one bin and 8 consecutive blocks, and slides a register window over
+// the rows: 2 shared loads per 32 FFMA.
+struct MacItem {
+    int64_t pair, j0, f0;
+    int pc;
+};
+__global__ void __launch_bounds__(512, 1) fir_mac_kernel(const float2 *__restrict__ Z, const float2 *__restrict__ H,
+                                                        float2 *__restrict__ Y, int P, int64_t nrows, int64_t ring0,
+                                                        int64_t nvalid, int64_t nout, int64_t ntiles_j, int64_t ntiles) {
     extern __shared__ float2 smc[];
-    float2 *Zs = smc;                        // [kMacRows][kMacBins]
-    float2 *Hs = smc + kMacRows * kMacBins;  // [kMacPc][kMacBins]
+    constexpr int kBufElems = (kMacRows + kMacPc) * kMacBins;  // Zs [95][64] then Hs [32][64]
     const int fl = threadIdx.x & (kMacBins - 1);
     const int kg = threadIdx.x >> 6;  // 0..7: which 8 consecutive blocks
-    const int64_t f0 = static_cast<int64_t>(blockIdx.x) * kMacBins;
-    const int64_t j0 = static_cast<int64_t>(blockIdx.y) * kMacBlocks;
-    const int64_t pair = blockIdx.z;
-    const float2 *Zp = Z + pair * nrows * kN;
-    float2 acc[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) acc[r] = make_float2(0.f, 0.f);
     const int nchunks = (P + kMacPc - 1) / kMacPc;
-    for (int pc = 0; pc < nchunks; ++pc) {
-        // rows needed: j + (P-1) - p for j in [j0, j0+64), p in [32pc, 32pc+32)
-        const int64_t row_lo = j0 + (P - 1) - (pc * kMacPc + kMacPc - 1);
-        __syncthreads();
-        for (int i = threadIdx.x; i < kMacRows * kMacBins; i += 512) {
-            const int r = i >> 6, f = i & (kMacBins - 1);
+
+    auto decode = [&](int64_t t, int pc) {
+        MacItem it;
+        it.pc = pc;
+        it.f0 = (t % (kN / kMacBins)) * kMacBins;
+        t /= (kN / kMacBins);
+        it.j0 = (t % ntiles_j) * kMacBlocks;
+        it.pair = t / ntiles_j;
+        return it;
+    };
+    // partitions of chunk pc that exist, rounded up to the unroll step of the short path
+    auto chunk_parts = [&](int pc) { return min(kMacPc, ((P - pc * kMacPc) + 7) & ~7); };
+    auto issue = [&](const MacItem &it, float2 *buf) {
+        const int npl = chunk_parts(it.pc);
+        const float2 *Zp = Z + it.pair * nrows * kN + it.f0;
+        // rows needed: j + (P-1) - p for j in [j0, j0+64), p in [32pc, 32pc+npl)
+        const int64_t row_lo = it.j0 + (P - 1) - (it.pc * kMacPc + kMacPc - 1);
+        const int r_first = kMacPc - npl;  // local rows below this belong to partitions that are not run
+        for (int i = threadIdx.x + r_first * 32; i < kMacRows * 32; i += 512) {
+            const int r = i >> 5, q = i & 31;  // 32 16-byte pieces per 64-bin row
             const int64_t row = row_lo + r;
-            Zs[i] = (row >= 0 && row < nrows) ? Zp[row * kN + f0 + f] : make_float2(0.f, 0.f);
+            const bool ok = row >= 0 && row < nvalid;
+            cp_async16_zfill(buf + r * kMacBins + 2 * q, Zp + (ok ? ring_slot(ring0, row, nrows) : 0) * kN + 2 * q, ok);
         }
-        for (int i = threadIdx.x; i < kMacPc * kMacBins; i += 512) {
-            const int pl = i >> 6, f = i & (kMacBins - 1);
-            const int p = pc * kMacPc + pl;
-            Hs[i] = p < P ? H[static_cast<int64_t>(p) * kN + f0 + f] : make_float2(0.f, 0.f);
+        float2 *hb = buf + kMacRows * kMacBins;
+        for (int i = threadIdx.x; i < npl * 32; i += 512) {
+            const int pl = i >> 5, q = i & 31;
+            const int p = it.pc * kMacPc + pl;
+            const bool ok = p < P;
+            cp_async16_zfill(hb + pl * kMacBins + 2 * q, H + static_cast<int64_t>(ok ? p : 0) * kN + it.f0 + 2 * q, ok);
+        }
+        cp_async_commit();
+    };
+
+    float2 acc[8];
+    // this CTA's work: tiles blockIdx.x, blockIdx.x + gridDim.x, ...; within a tile chunks 0..nchunks-1
+    int64_t tile = blockIdx.x;
+    int pc = 0;
+    if (tile >= ntiles) return;
+    MacItem cur = decode(tile, pc);
+    int b = 0;
+    issue(cur, smc);
+    while (tile < ntiles) {
+        int64_t ntile = tile;
+        int npc = pc + 1;
+        if (npc == nchunks) {
+            npc = 0;
+            ntile = tile + gridDim.x;
+        }
+        MacItem nxt = cur;
+        if (ntile < ntiles) {
+            nxt = decode(ntile, npc);
+            issue(nxt, smc + (b ^ 1) * kBufElems);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncthreads();
-        // local row of (block jj, partition pl) = kg*8 + jj + 31 - pl = m0 + jj - pl, m0 = kg*8 + 31
-        const float2 *zcol = Zs + fl;
-        const int m0 = kg * 8 + (kMacPc - 1);
-        float2 w[8];  // w[m & 7] = Zs[m0 + m - pl] window, m = jj
+        if (cur.pc == 0) {
 #pragma unroll
-        for (int m = 0; m < 8; ++m) w[m] = zcol[(m0 + m) * kMacBins];
+            for (int r = 0; r < 8; ++r) acc[r] = make_float2(0.f, 0.f);
+        }
+        {
+            const float2 *Zs = smc + b * kBufElems;
+            const float2 *Hs = Zs + kMacRows * kMacBins;
+            // local row of (block jj, partition pl) = kg*8 + jj + 31 - pl = m0 + jj - pl, m0 = kg*8 + 31
+            const float2 *zcol = Zs + fl;
+            const int m0 = kg * 8 + (kMacPc - 1);
+            const int npl = chunk_parts(cur.pc);
+            float2 w[8];  // w[m & 7] = Zs[m0 + m - pl] window, m = jj
 #pragma unroll
-        for (int pl = 0; pl < kMacPc; ++pl) {
-            const float2 h = Hs[pl * kMacBins + fl];
+            for (int m = 0; m < 8; ++m) w[m] = zcol[(m0 + m) * kMacBins];
+            if (npl == kMacPc) {
+#pragma unroll
+                for (int pl = 0; pl < kMacPc; ++pl) {
+                    const float2 h = Hs[pl * kMacBins + fl];
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const float2 z = w[(jj - pl) & 7];
+                        acc[jj].x = fmaf(h.x, z.x, acc[jj].x);
+                        acc[jj].x = fmaf(-h.y, z.y, acc[jj].x);
+                        acc[jj].y = fmaf(h.x, z.y, acc[jj].y);
+                        acc[jj].y = fmaf(h.y, z.x, acc[jj].y);
+                    }
+                    if (pl + 1 < kMacPc) w[(7 - pl) & 7] = zcol[(m0 - pl - 1) * kMacBins];
+                }
+            } else {
+                // short chunk (P not a multiple of 32): 8 partitions per unrolled step keep the window
+                // indices compile-time; P = 1 costs 1/4 of a full chunk instead of all of it
+                for (int pb = 0; pb < npl; pb += 8) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int pl = pb + u;
+                        const float2 h = Hs[pl * kMacBins + fl];
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            const float2 z = w[(jj - u) & 7];
+                            acc[jj].x = fmaf(h.x, z.x, acc[jj].x);
+                            acc[jj].x = fmaf(-h.y, z.y, acc[jj].x);
+                            acc[jj].y = fmaf(h.x, z.y, acc[jj].y);
+                            acc[jj].y = fmaf(h.y, z.x, acc[jj].y);
+                        }
+                        if (pl + 1 < npl) w[(7 - u) & 7] = zcol[(m0 - pl - 1) * kMacBins];
+                    }
+                }
+            }
+        }
+        if (cur.pc == nchunks - 1) {
+            float2 *Yp = Y + cur.pair * nout * kN + cur.f0 + fl;
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
-                const float2 z = w[(jj - pl) & 7];
-                acc[jj].x = fmaf(h.x, z.x, acc[jj].x);
-                acc[jj].x = fmaf(-h.y, z.y, acc[jj].x);
-                acc[jj].y = fmaf(h.x, z.y, acc[jj].y);
-                acc[jj].y = fmaf(h.y, z.x, acc[jj].y);
+                const int64_t j = cur.j0 + kg * 8 + jj;
+                if (j < nout) Yp[j * kN] = acc[jj];
             }
-            if (pl + 1 < kMacPc) w[(7 - pl) & 7] = zcol[(m0 - pl - 1) * kMacBins];
         }
-    }
-    float2 *Yp = Y + pair * nout * kN;
-#pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
-        const int64_t j = j0 + kg * 8 + jj;
-        if (j < nout) Yp[j * kN + f0 + fl] = acc[jj];
+        __syncthreads();  // buffer b is free for the fetch issued in the next iteration
+        cur = nxt;
+        tile = ntile;
+        pc = npc;
+        b ^= 1;
     }
 }
 
 // y[kB : (k+1)B] of both channels of the pair = IFFT(Y[pair][j])[B : 2B] / N,  k = k_first + j
 __global__ void __launch_bounds__(kFftThreads) fir_inv_kernel(const float2 *__restrict__ Y, float *__restrict__ y, int64_t C, int64_t T,
                                                              int64_t ldy, int64_t k_first, int64_t nout,
-                                                             const float2 *__restrict__ tw) {
+                                                             const float4 *__restrict__ tab) {
     __shared__ float2 s[kPadN];
     const int64_t j = blockIdx.x;
     const int64_t pair = blockIdx.y;
-    const float2 *in = Y + (pair * nout + j) * kN;
-    {   // all 16 loads of a thread in flight before the first shared-memory store
-        float2 r[kN / kFftThreads];
-#pragma unroll
-        for (int u = 0; u < kN / kFftThreads; ++u) r[u] = __ldcs(&in[threadIdx.x + u * kFftThreads]);
-#pragma unroll
-        for (int u = 0; u < kN / kFftThreads; ++u) s[pidx(threadIdx.x + u * kFftThreads)] = r[u];
-    }
-    __syncthreads();
-    fft_dit4_inv(s, tw);
+    float2 v[16];
+    fft_inv(v, s, tab, Y + (pair * nout + j) * kN);
+    // v[m] = time sample threadIdx.x + 256 m of the block; the valid half is m >= 8
     const int64_t ca = 2 * pair, cb = 2 * pair + 1;
-    const int64_t nbase = (k_first + j) * kB;
+    const int64_t nbase = (k_first + j) * kB + threadIdx.x;
     const float scale = 1.0f / kN;
-    for (int i = threadIdx.x; i < kB; i += kFftThreads) {
-        const int64_t n = nbase + i;
+    float *ya = y + ca * ldy;
+    float *yb = y + cb * ldy;
+    const bool has_b = cb < C;
+#pragma unroll
+    for (int m = 8; m < 16; ++m) {
+        const int64_t n = nbase + 256 * (m - 8);
         if (n < T) {
-            const float2 v = s[pidx(kB + i)];
-            y[ca * ldy + n] = v.x * scale;
-            if (cb < C) y[cb * ldy + n] = v.y * scale;
+            ya[n] = v[m].x * scale;
+            if (has_b) yb[n] = v[m].y * scale;
         }
     }
 }
@@ -456,36 +604,33 @@ int tfx_fir_f32(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int
     }
     TFX_REQUIRE(L.P <= 65535 && L.npairs <= 65535, "fir: too many partitions / channel pairs for one launch");
     unsigned char *ws = static_cast<unsigned char *>(workspace);
-    float2 *tw = reinterpret_cast<float2 *>(ws + L.off_tw);
+    float2 *tw2 = reinterpret_cast<float2 *>(ws + L.off_tw);
+    const float4 *tw = reinterpret_cast<const float4 *>(tw2);
     float2 *H = reinterpret_cast<float2 *>(ws + L.off_H);
     float2 *Z = reinterpret_cast<float2 *>(ws + L.off_Z);
     float2 *Y = reinterpret_cast<float2 *>(ws + L.off_Y);
-    fir_twiddle_kernel<<<kN / 256, 256, 0, stream>>>(tw);
+    fir_twiddle_kernel<<<(kTwEntries + 255) / 256, 256, 0, stream>>>(tw2);
     TFX_CHECK_LAUNCH("fir_twiddle_kernel");
     fir_taps_fft_kernel<<<static_cast<unsigned>(L.P), kFftThreads, 0, stream>>>(taps, K, H, tw);
     TFX_CHECK_LAUNCH("fir_taps_fft_kernel");
-    const size_t mac_smem = sizeof(float2) * (kMacRows + kMacPc) * kMacBins;
+    const size_t mac_smem = 2 * sizeof(float2) * (kMacRows + kMacPc) * kMacBins;  // double buffer
     TFX_ENSURE_SMEM(fir_mac_kernel, static_cast<int>(mac_smem));
-    const size_t row_bytes = sizeof(float2) * kN;
     for (int64_t k0 = 0; k0 < L.nblk; k0 += L.slab) {
         const int64_t nout = std::min<int64_t>(L.slab, L.nblk - k0);
         const int64_t nrows = L.nrows;  // row pitch of Z per pair, the same for every slab
         const int64_t k_first = k0 - (L.P - 1);
-        // The P-1 history spectra of this slab are the last P-1 rows of the previous one: move them
-        // to the front (device-to-device, ~1 % of a slab's traffic) instead of transforming the
-        // same input blocks again; the first slab's history (k < 0) is written as zeros by the kernel.
-        int64_t row0 = 0;
-        if (k0 > 0 && L.P > 1) {
-            row0 = L.P - 1;
-            TFX_CUDA_TRY(cudaMemcpy2DAsync(Z, nrows * row_bytes, Z + L.slab * kN, nrows * row_bytes, row0 * row_bytes,
-                                           static_cast<size_t>(L.npairs), cudaMemcpyDeviceToDevice, stream));
-        }
+        // The P-1 history spectra of this slab are the last P-1 of the previous one and are still in the
+        // ring: only the new blocks are transformed.  The first slab's history (k < 0) is written as zeros.
+        const int64_t row0 = k0 > 0 ? L.P - 1 : 0;
+        const int64_t ring0 = k0 % nrows;
         fir_fwd_kernel<<<dim3(static_cast<unsigned>(nout + L.P - 1 - row0), static_cast<unsigned>(L.npairs)), kFftThreads, 0,
-                         stream>>>(x, C, T, ldx, k_first, nrows, row0, Z, tw);
+                         stream>>>(x, C, T, ldx, k_first, nrows, row0, ring0, Z, tw);
         TFX_CHECK_LAUNCH("fir_fwd_kernel");
-        fir_mac_kernel<<<dim3(kN / kMacBins, static_cast<unsigned>((nout + kMacBlocks - 1) / kMacBlocks),
-                              static_cast<unsigned>(L.npairs)),
-                         512, mac_smem, stream>>>(Z, H, Y, static_cast<int>(L.P), nrows, nout);
+        const int64_t ntiles_j = (nout + kMacBlocks - 1) / kMacBlocks;
+        const int64_t ntiles = L.npairs * ntiles_j * (kN / kMacBins);
+        const unsigned mac_grid = static_cast<unsigned>(std::min<int64_t>(ntiles, sm_count()));
+        fir_mac_kernel<<<mac_grid, 512, mac_smem, stream>>>(Z, H, Y, static_cast<int>(L.P), nrows, ring0, nout + L.P - 1, nout,
+                                                          ntiles_j, ntiles);
         TFX_CHECK_LAUNCH("fir_mac_kernel");
         fir_inv_kernel<<<dim3(static_cast<unsigned>(nout), static_cast<unsigned>(L.npairs)), kFftThreads, 0, stream>>>(
             Y, y, C, T, ldy, k0, nout, tw);
