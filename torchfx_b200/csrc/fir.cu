@@ -42,9 +42,10 @@ constexpr int kN = 4096;              // complex FFT size
 constexpr int kB = 2048;              // partition / hop
 constexpr int kFftThreads = 256;
 constexpr int kMacBins = 64;          // bins per MAC CTA
-constexpr int kMacBlocks = 64;        // output blocks per MAC CTA
+constexpr int kMacBlocks = 128;       // output blocks per MAC tile
+constexpr int kMacPerThread = 16;     // consecutive blocks per thread (512 threads = 64 bins x 8 groups)
 constexpr int kMacPc = 32;            // partitions per shared-memory chunk
-constexpr int kMacRows = kMacBlocks + kMacPc - 1;  // 95 spectra rows staged per chunk
+constexpr int kMacRows = kMacBlocks + kMacPc - 1;  // 159 spectra rows staged per chunk
 
 // ------------------------------------------------------------------------------------------
 // DIRECT
@@ -358,28 +359,28 @@ __device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gme
 
 // Y[pair][j] = sum_p H[p] . Z[pair][j + (P-1) - p],  j in [0, nout)
 //
-// Persistent CTAs (one per SM, 512 threads) walk the (pair, 64-block, 64-bin) tiles; a tile with
+// Persistent CTAs (one per SM, 512 threads) walk the (pair, 128-block, 64-bin) tiles; a tile with
 // P > 32 partitions is a run of 32-partition work items that accumulate in registers.  The
-// [95 x 64] spectra rows and [32 x 64] taps of item i+1 are fetched with cp.async into the other
+// [159 x 64] spectra rows and [32 x 64] taps of item i+1 are fetched with cp.async into the other
 // half of a double buffer while item i is multiplied, so the FMA pipe never waits on a staging phase
 // (the first version loaded, synchronised and then computed with two CTAs per SM: 39 % FMA
 // utilisation, `long_scoreboard` the dominant stall).
-// Inner loop: each thread owns one bin and 8 consecutive blocks, and slides a register window over
-// the rows: 2 shared loads per 32 FFMA.
+// Inner loop: each thread owns one bin and kMacPerThread = 16 consecutive blocks and slides a
+// register window over the rows: 2 shared loads per 64 FFMA.
 struct MacItem {
-    int64_t pair, j0, f0;
-    int pc;
+    int pair, j0, f0, pc;
 };
 __global__ void __launch_bounds__(512, 1) fir_mac_kernel(const float2 *__restrict__ Z, const float2 *__restrict__ H,
-                                                        float2 *__restrict__ Y, int P, int64_t nrows, int64_t ring0,
-                                                        int64_t nvalid, int64_t nout, int64_t ntiles_j, int64_t ntiles) {
+                                                        float2 *__restrict__ Y, int P, int nrows, int ring0, int nvalid,
+                                                        int nout, int ntiles_j, int ntiles) {
     extern __shared__ float2 smc[];
-    constexpr int kBufElems = (kMacRows + kMacPc) * kMacBins;  // Zs [95][64] then Hs [32][64]
+    constexpr int kBufElems = (kMacRows + kMacPc) * kMacBins;  // Zs [159][64] then Hs [32][64]
+    constexpr int R = kMacPerThread;
     const int fl = threadIdx.x & (kMacBins - 1);
-    const int kg = threadIdx.x >> 6;  // 0..7: which 8 consecutive blocks
+    const int kg = threadIdx.x >> 6;  // 0..7: which R consecutive blocks
     const int nchunks = (P + kMacPc - 1) / kMacPc;
 
-    auto decode = [&](int64_t t, int pc) {
+    auto decode = [&](int t, int pc) {
         MacItem it;
         it.pc = pc;
         it.f0 = (t % (kN / kMacBins)) * kMacBins;
@@ -392,36 +393,38 @@ __global__ void __launch_bounds__(512, 1) fir_mac_kernel(const float2 *__restric
     auto chunk_parts = [&](int pc) { return min(kMacPc, ((P - pc * kMacPc) + 7) & ~7); };
     auto issue = [&](const MacItem &it, float2 *buf) {
         const int npl = chunk_parts(it.pc);
-        const float2 *Zp = Z + it.pair * nrows * kN + it.f0;
-        // rows needed: j + (P-1) - p for j in [j0, j0+64), p in [32pc, 32pc+npl)
-        const int64_t row_lo = it.j0 + (P - 1) - (it.pc * kMacPc + kMacPc - 1);
+        const float2 *Zp = Z + static_cast<int64_t>(it.pair) * nrows * kN + it.f0;
+        // rows needed: j + (P-1) - p for j in [j0, j0 + kMacBlocks), p in [32pc, 32pc+npl)
+        const int row_lo = it.j0 + (P - 1) - (it.pc * kMacPc + kMacPc - 1);
         const int r_first = kMacPc - npl;  // local rows below this belong to partitions that are not run
         for (int i = threadIdx.x + r_first * 32; i < kMacRows * 32; i += 512) {
             const int r = i >> 5, q = i & 31;  // 32 16-byte pieces per 64-bin row
-            const int64_t row = row_lo + r;
+            const int row = row_lo + r;
             const bool ok = row >= 0 && row < nvalid;
-            cp_async16_zfill(buf + r * kMacBins + 2 * q, Zp + (ok ? ring_slot(ring0, row, nrows) : 0) * kN + 2 * q, ok);
+            int slot = ring0 + row;
+            slot = slot >= nrows ? slot - nrows : slot;
+            cp_async16_zfill(buf + r * kMacBins + 2 * q, Zp + (ok ? slot * kN : 0) + 2 * q, ok);
         }
         float2 *hb = buf + kMacRows * kMacBins;
         for (int i = threadIdx.x; i < npl * 32; i += 512) {
             const int pl = i >> 5, q = i & 31;
             const int p = it.pc * kMacPc + pl;
             const bool ok = p < P;
-            cp_async16_zfill(hb + pl * kMacBins + 2 * q, H + static_cast<int64_t>(ok ? p : 0) * kN + it.f0 + 2 * q, ok);
+            cp_async16_zfill(hb + pl * kMacBins + 2 * q, H + (ok ? p * kN : 0) + it.f0 + 2 * q, ok);
         }
         cp_async_commit();
     };
 
-    float2 acc[8];
+    float2 acc[R];
     // this CTA's work: tiles blockIdx.x, blockIdx.x + gridDim.x, ...; within a tile chunks 0..nchunks-1
-    int64_t tile = blockIdx.x;
+    int tile = blockIdx.x;
     int pc = 0;
     if (tile >= ntiles) return;
     MacItem cur = decode(tile, pc);
     int b = 0;
     issue(cur, smc);
     while (tile < ntiles) {
-        int64_t ntile = tile;
+        int ntile = tile;
         int npc = pc + 1;
         if (npc == nchunks) {
             npc = 0;
@@ -438,31 +441,31 @@ __global__ void __launch_bounds__(512, 1) fir_mac_kernel(const float2 *__restric
         __syncthreads();
         if (cur.pc == 0) {
 #pragma unroll
-            for (int r = 0; r < 8; ++r) acc[r] = make_float2(0.f, 0.f);
+            for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
         }
         {
             const float2 *Zs = smc + b * kBufElems;
             const float2 *Hs = Zs + kMacRows * kMacBins;
-            // local row of (block jj, partition pl) = kg*8 + jj + 31 - pl = m0 + jj - pl, m0 = kg*8 + 31
+            // local row of (block jj, partition pl) = kg*R + jj + 31 - pl = m0 + jj - pl, m0 = kg*R + 31
             const float2 *zcol = Zs + fl;
-            const int m0 = kg * 8 + (kMacPc - 1);
+            const int m0 = kg * R + (kMacPc - 1);
             const int npl = chunk_parts(cur.pc);
-            float2 w[8];  // w[m & 7] = Zs[m0 + m - pl] window, m = jj
+            float2 w[R];  // w[m & (R-1)] = Zs[m0 + m - pl] window, m = jj
 #pragma unroll
-            for (int m = 0; m < 8; ++m) w[m] = zcol[(m0 + m) * kMacBins];
+            for (int m = 0; m < R; ++m) w[m] = zcol[(m0 + m) * kMacBins];
             if (npl == kMacPc) {
 #pragma unroll
                 for (int pl = 0; pl < kMacPc; ++pl) {
                     const float2 h = Hs[pl * kMacBins + fl];
 #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        const float2 z = w[(jj - pl) & 7];
+                    for (int jj = 0; jj < R; ++jj) {
+                        const float2 z = w[(jj - pl) & (R - 1)];
                         acc[jj].x = fmaf(h.x, z.x, acc[jj].x);
                         acc[jj].x = fmaf(-h.y, z.y, acc[jj].x);
                         acc[jj].y = fmaf(h.x, z.y, acc[jj].y);
                         acc[jj].y = fmaf(h.y, z.x, acc[jj].y);
                     }
-                    if (pl + 1 < kMacPc) w[(7 - pl) & 7] = zcol[(m0 - pl - 1) * kMacBins];
+                    if (pl + 1 < kMacPc) w[(R - 1 - pl) & (R - 1)] = zcol[(m0 - pl - 1) * kMacBins];
                 }
             } else {
                 // short chunk (P not a multiple of 32): 8 partitions per unrolled step keep the window
@@ -473,24 +476,30 @@ __global__ void __launch_bounds__(512, 1) fir_mac_kernel(const float2 *__restric
                         const int pl = pb + u;
                         const float2 h = Hs[pl * kMacBins + fl];
 #pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) {
-                            const float2 z = w[(jj - u) & 7];
+                        for (int jj = 0; jj < R; ++jj) {
+                            const float2 z = w[(jj - u) & (R - 1)];
                             acc[jj].x = fmaf(h.x, z.x, acc[jj].x);
                             acc[jj].x = fmaf(-h.y, z.y, acc[jj].x);
                             acc[jj].y = fmaf(h.x, z.y, acc[jj].y);
                             acc[jj].y = fmaf(h.y, z.x, acc[jj].y);
                         }
-                        if (pl + 1 < npl) w[(7 - u) & 7] = zcol[(m0 - pl - 1) * kMacBins];
+                        if (pl + 1 < npl) w[(R - 1 - u) & (R - 1)] = zcol[(m0 - pl - 1) * kMacBins];
+                    }
+                    // after 8 partitions the window has slid 8 rows: rotate the register names back
+                    // the window has slid 8 rows but holds 16: reload it rather than rotate register names
+                    if (pb + 8 < npl) {
+#pragma unroll
+                        for (int m = 0; m < R; ++m) w[m] = zcol[(m0 + m - (pb + 8)) * kMacBins];
                     }
                 }
             }
         }
         if (cur.pc == nchunks - 1) {
-            float2 *Yp = Y + cur.pair * nout * kN + cur.f0 + fl;
+            float2 *Yp = Y + static_cast<int64_t>(cur.pair) * nout * kN + cur.f0 + fl;
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-                const int64_t j = cur.j0 + kg * 8 + jj;
-                if (j < nout) Yp[j * kN] = acc[jj];
+            for (int jj = 0; jj < R; ++jj) {
+                const int j = cur.j0 + kg * R + jj;
+                if (j < nout) Yp[static_cast<int64_t>(j) * kN] = acc[jj];
             }
         }
         __syncthreads();  // buffer b is free for the fetch issued in the next iteration
@@ -628,9 +637,12 @@ int tfx_fir_f32(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int
         TFX_CHECK_LAUNCH("fir_fwd_kernel");
         const int64_t ntiles_j = (nout + kMacBlocks - 1) / kMacBlocks;
         const int64_t ntiles = L.npairs * ntiles_j * (kN / kMacBins);
+        TFX_REQUIRE(ntiles < (int64_t(1) << 31) && nrows < (int64_t(1) << 19), "fir: slab too large for the MAC kernel's 32-bit indexing");
         const unsigned mac_grid = static_cast<unsigned>(std::min<int64_t>(ntiles, sm_count()));
-        fir_mac_kernel<<<mac_grid, 512, mac_smem, stream>>>(Z, H, Y, static_cast<int>(L.P), nrows, ring0, nout + L.P - 1, nout,
-                                                          ntiles_j, ntiles);
+        fir_mac_kernel<<<mac_grid, 512, mac_smem, stream>>>(Z, H, Y, static_cast<int>(L.P), static_cast<int>(nrows),
+                                                          static_cast<int>(ring0), static_cast<int>(nout + L.P - 1),
+                                                          static_cast<int>(nout), static_cast<int>(ntiles_j),
+                                                          static_cast<int>(ntiles));
         TFX_CHECK_LAUNCH("fir_mac_kernel");
         fir_inv_kernel<<<dim3(static_cast<unsigned>(nout), static_cast<unsigned>(L.npairs)), kFftThreads, 0, stream>>>(
             Y, y, C, T, ldy, k0, nout, tw);
