@@ -98,3 +98,90 @@ def test_f64_io():
     bank.compute_coefficients()
     want = oracle.filterbank_stack(x, np.stack([f._sos.numpy() for f in bank.filters]))
     np.testing.assert_allclose(y.cpu().numpy(), want, rtol=1e-9, atol=1e-11)
+
+
+# ---- SUM banks on the channel-tile kernel (bank_tile.cu: parallel topology, lanes = channels) -----------
+
+def _sum_bank(n, kb, fs=48000):
+    if kb == 1:
+        return [fx.filter.BiquadBPF(300.0 * (1.6 ** i), 1.414, fs) for i in range(n)]
+    return [fx.filter.LoButterworth(800.0 * (1.5 ** i), order=4, fs=fs) for i in range(n)]
+
+
+@pytest.mark.parametrize("n,kb", [(2, 1), (3, 1), (5, 1), (7, 1), (8, 1), (2, 2), (3, 2), (4, 2)])
+@pytest.mark.parametrize("C", [32, 61])
+def test_sum_tile_vs_oracle(n, kb, C):
+    from torchfx_b200.filter._sosbank import SosBank
+
+    rng = np.random.default_rng(100 * n + kb + C)
+    T = 70001  # odd length: ragged last chunk, split in time (warm-up launch + work counter)
+    x = (0.1 * rng.standard_normal((C, T))).astype(np.float32)
+    filters = _sum_bank(n, kb)
+    bank = SosBank(filters, mode="sum")
+    before = _native.kernel_launches()
+    y = bank(torch.from_numpy(x).to(DEV)).cpu().numpy()
+    assert _native.kernel_launches() - before <= 2  # warm-up + main, not n launches
+    sos = np.stack([f._sos.numpy() for f in filters])
+    want = oracle.filterbank_sum(x, sos)
+    assert rel_to_max(y, want) < TOL
+    # the stream-per-lane bank kernel and the unsplit tile kernel agree with it
+    for flags in (_native.TFX_NO_TILE, _native.TFX_NO_SPLIT):
+        other = SosBank(_sum_bank(n, kb), mode="sum")
+        other.flags = flags
+        y2 = other(torch.from_numpy(x).to(DEV)).cpu().numpy()
+        assert rel_to_max(y2, y) < 2e-6
+    # children own the DF1 state a solo run would have left
+    i = n // 2
+    _, wsx, wsy = oracle.sos_cascade(x, sos[i])
+    np.testing.assert_allclose(filters[i]._state_x.cpu().numpy(), wsx, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(filters[i]._state_y.cpu().numpy(), wsy, rtol=1e-3, atol=1e-5 * np.abs(wsy).max())
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64", "auto"])
+def test_sum_tile_chunked_state_and_precisions(precision):
+    """`f1 + f2 + ...` over 64 channels, fed in three uneven chunks: state carries exactly as
+    with separately-run children (reference tests/test_fused.py:185-200 contract)."""
+    from torchfx_b200 import _ops
+
+    rng = np.random.default_rng(77)
+    x = (0.1 * rng.standard_normal((64, 90000))).astype(np.float32)
+
+    def make():
+        return [fx.filter.BiquadBPF(250, 1.414, 48000), fx.filter.BiquadBPF(40, 1.414, 48000), fx.filter.BiquadLPF(6000, 0.707, 48000),
+                fx.filter.BiquadHPF(90, 0.707, 48000)]
+
+    comb = fx.filter._base.ParallelFilterCombination(*make())
+    xt = torch.from_numpy(x).to(DEV)
+    old = _ops.get_default_precision()
+    _ops.set_default_precision(precision)
+    try:
+        y = torch.cat([comb(xt[:, :1]), comb(xt[:, 1:40003]), comb(xt[:, 40003:])], dim=1).cpu().numpy()
+    finally:
+        _ops.set_default_precision(old)
+    want = np.zeros_like(x)
+    for f in make():
+        f.compute_coefficients()
+        want += oracle.sos_cascade(x, f._sos.numpy())[0]
+    assert rel_to_max(y, want) < (2e-4 if precision == "f32" else TOL)  # 40 Hz band: float32 recurrence is not 1e-5 accurate
+
+
+def test_sum_tile_full_size_linearity():
+    """Config-5 secondary shape (8 BiquadBPF over 1024 channels) at a size the oracle cannot
+    cover: linearity, bank(a*x1 + x2) == a*bank(x1) + bank(x2), and oracle parity on 4 channels."""
+    from torchfx_b200.filter._sosbank import SosBank
+
+    C, T = 1024, 480000
+    g = torch.Generator(device=DEV).manual_seed(11)
+    x1 = 0.1 * torch.randn(C, T, device=DEV, generator=g)
+    x2 = 0.1 * torch.randn(C, T, device=DEV, generator=g)
+    def run(x):
+        return SosBank(_sum_bank(8, 1), mode="sum")(x)
+    y1, y2, y12 = run(x1), run(x2), run(0.5 * x1 + x2)
+    err = (y12 - (0.5 * y1 + y2)).abs().max().item() / y12.abs().max().item()
+    assert err < 5e-6
+    sel = [0, 333, 777, 1023]
+    filters = _sum_bank(8, 1)
+    for f in filters:
+        f.compute_coefficients()
+    want = oracle.filterbank_sum(x1[sel].cpu().numpy(), np.stack([f._sos.numpy() for f in filters]))
+    assert rel_to_max(y1[sel].cpu().numpy(), want) < TOL

@@ -140,11 +140,14 @@ def cfg5():
     C, T, N = 256, int(SECONDS * FS), 32
     x = torch.empty((C, T), device=DEV).normal_(0, 0.1)
     bank = fx.filter.LogFilterBank(n_bands=N, f_min=20.0, f_max=20000.0, q=1.414, fs=FS)
-    ms, nl = timed(lambda: (bank.reset_state(), bank(x))[1], reps=3)
     lanes = N * C * T
     bytes_alg = 4 * lanes * (1 + 1 / N)
-    out["stack"] = {"ms": round(ms, 3), "G_lane_samples_s": round(lanes / ms / 1e6, 1), "GBps": round(bytes_alg / ms / 1e6, 1),
-                    "frac_hbm": round(bytes_alg / ms / 1e6 / PEAK, 3), "launches": nl, "shape": [N, C, T]}
+    for prec in ("f32", "f64", "auto"):
+        _ops.set_default_precision(prec)
+        ms, nl = timed(lambda: (bank.reset_state(), bank(x))[1], reps=3)
+        out["stack" if prec == "auto" else f"stack_{prec}"] = {
+            "ms": round(ms, 3), "G_lane_samples_s": round(lanes / ms / 1e6, 1), "GBps": round(bytes_alg / ms / 1e6, 1),
+            "frac_hbm": round(bytes_alg / ms / 1e6 / PEAK, 3), "launches": nl, "shape": [N, C, T]}
     bank.reset_state()
     y = bank(x[:2, : 1 << 17])
     bank.compute_coefficients()
@@ -160,9 +163,12 @@ def cfg5():
         for f in fl:
             f.reset_state()
         return comb(x)
-    ms, nl = timed(run_sum, reps=3)
-    out["sum"] = {"ms": round(ms, 3), "Gsamples_s": round(C * T / ms / 1e6, 1), "G_lane_samples_s": round(8 * C * T / ms / 1e6, 1),
-                  "GBps": round(8 * C * T / ms / 1e6, 1), "frac_hbm": round(8 * C * T / ms / 1e6 / PEAK, 3), "launches": nl}
+    for prec in ("f32", "f64", "auto"):
+        _ops.set_default_precision(prec)
+        ms, nl = timed(run_sum, reps=3)
+        out["sum" if prec == "auto" else f"sum_{prec}"] = {
+            "ms": round(ms, 3), "Gsamples_s": round(C * T / ms / 1e6, 1), "G_lane_samples_s": round(8 * C * T / ms / 1e6, 1),
+            "GBps": round(8 * C * T / ms / 1e6, 1), "frac_hbm": round(8 * C * T / ms / 1e6 / PEAK, 3), "launches": nl}
     for f in fl:
         f.reset_state()
     y = comb(x[:2, : 1 << 17])

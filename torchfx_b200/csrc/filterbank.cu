@@ -18,7 +18,9 @@
 #include <cstdint>
 #include <vector>
 
+#include "bank_tile.h"
 #include "common.cuh"
+#include "sos_kernels.h"
 #include "sos_plan.h"
 #include "stream_common.cuh"
 
@@ -437,6 +439,43 @@ int filterbank_device(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, int
     int rc = require_device();
     if (rc != TFX_OK) return rc;
 
+    // SUM banks of up to 8 sections with enough channels: the channel-tile kernel with the parallel
+    // topology (bank_tile.cu) -- x read once, y written once, branch states in registers.
+    if constexpr (sizeof(IO) == 4) {
+        if (mode == TFX_BANK_SUM && !(flags & TFX_NO_TILE) && bank_sum_tile_ok(N, Kb, C)) {
+            uint32_t prec = flags & TFX_PREC_MASK;
+            if (prec == TFX_PREC_AUTO) {
+                prec = TFX_PREC_F32;
+                for (int b = 0; b < N; ++b)
+                    if (plans[b]->auto_prec == TFX_PREC_F64) prec = TFX_PREC_F64;
+            }
+            TFX_REQUIRE(prec == TFX_PREC_F32 || prec == TFX_PREC_F64, "filterbank: bad precision flag");
+            int64_t warm_needed = 0;
+            std::vector<SosSection> sec;
+            for (int b = 0; b < N; ++b) {
+                const SosPass &p = plans[b]->passes[0];
+                const int64_t w = prec == TFX_PREC_F32 ? p.warm_f32 : p.warm_f64_io32;
+                warm_needed = (w < 0 || warm_needed < 0) ? -1 : std::max(warm_needed, w);
+                for (int k = 0; k < Kb; ++k) sec.push_back(plans[b]->sec[k]);
+            }
+            const int64_t lanes = (C + 31) / 32 * 32;
+            const Segmentation seg =
+                choose_segmentation(lanes, T, warm_needed, bank_tile_stream_capacity(), (flags & TFX_NO_SPLIT) != 0, kOversub);
+            if (seg.S > 1) {
+                const size_t need = kWsHeader + static_cast<size_t>(2 * N * Kb) * static_cast<size_t>(C * seg.S) * (prec == TFX_PREC_F32 ? 4 : 8);
+                if (workspace == nullptr || workspace_bytes < need) {
+                    set_error("filterbank: workspace of %zu bytes needed, %zu given (query tfx_filterbank_workspace_bytes)", need,
+                              workspace_bytes);
+                    return TFX_EWORKSPACE;
+                }
+            }
+            cudaStream_t st = static_cast<cudaStream_t>(stream_v);
+            if (prec == TFX_PREC_F32)
+                return launch_bank_sum_tile<float>(x, y, C, T, ldx, ldy, sec.data(), N, Kb, seg, workspace, state_x, state_y, st);
+            return launch_bank_sum_tile<double>(x, y, C, T, ldx, ldy, sec.data(), N, Kb, seg, workspace, state_x, state_y, st);
+        }
+    }
+
     // Precision per band.  With TFX_PREC_AUTO the bank is split by the per-band probe: bands whose
     // float32 recurrence is accurate run in a float32 launch, the others (low corners) in a
     // float64 launch -- the lanes of one launch execute one instruction stream, so mixing would
@@ -540,7 +579,11 @@ size_t tfx_filterbank_workspace_bytes(int64_t C, int64_t T, int N, int Kb) {
     // S > 1 only when C*S fits one wave of streams (at most SMs*8*16 with 2 lanes per stream).
     const int64_t streams = static_cast<int64_t>(tfx::sm_count()) * tfx::kMaxCtasPerSm * tfx::kWarps * tfx::kMaxSpw + 128;
     const int nb = N < 32 ? N : 32;
-    return static_cast<size_t>(2 * Kb * nb) * static_cast<size_t>(streams) * 8 + 256;
+    const size_t stream_path = static_cast<size_t>(2 * Kb * nb) * static_cast<size_t>(streams) * 8 + 256;
+    // channel-tile SUM path (bank_tile.cu): up to 8 sections, kOversub work items per resident warp
+    const int64_t tile_streams = tfx::bank_tile_stream_capacity() * tfx::kOversub + C + 128;
+    const size_t tile_path = tfx::bank_sum_tile_ok(N, Kb, C) ? tfx::kWsHeader + static_cast<size_t>(2 * N * Kb) * static_cast<size_t>(tile_streams) * 8 + 256 : 0;
+    return std::max(stream_path, tile_path);
 }
 
 int tfx_filterbank_f32(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, int64_t ldb,

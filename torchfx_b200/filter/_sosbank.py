@@ -36,6 +36,7 @@ class SosBank:
         self._state_y: Tensor | None = None
         self._sos_key: tuple | None = None
         self._sos: Tensor | None = None
+        self.flags = 0  # extra TFX_* kernel-selection flags (tests: TFX_NO_TILE, TFX_NO_SPLIT)
 
     def _gather_sos(self) -> Tensor | None:
         rows = []
@@ -110,7 +111,7 @@ class SosBank:
                 fn(x2.data_ptr(), y.data_ptr(), C, T, ldx, max(T, 1), ldb, sos.data_ptr(), n, kb,
                    N.TFX_BANK_SUM if self.mode == "sum" else N.TFX_BANK_STACK,
                    self._state_x.data_ptr(), self._state_y.data_ptr(),
-                   _ops._PRECISIONS[_ops.get_default_precision()], ws_ptr, ws_bytes,
+                   _ops._PRECISIONS[_ops.get_default_precision()] | self.flags, ws_ptr, ws_bytes,
                    torch.cuda.current_stream(x2.device).cuda_stream)
             )
         for i, f in enumerate(self.filters):
