@@ -185,3 +185,93 @@ def test_sum_tile_full_size_linearity():
         f.compute_coefficients()
     want = oracle.filterbank_sum(x1[sel].cpu().numpy(), np.stack([f._sos.numpy() for f in filters]))
     assert rel_to_max(y1[sel].cpu().numpy(), want) < TOL
+
+
+# ---- STACK banks with lanes = channels (bank_stack.cu: per-band precision and warm-up) ------------------
+
+@pytest.mark.parametrize("n_bands", [1, 3, 8, 12, 32, 40])
+@pytest.mark.parametrize("C", [32, 61])
+def test_stack_tile_vs_oracle(n_bands, C):
+    from torchfx_b200.filter._sosbank import SosBank
+
+    rng = np.random.default_rng(1000 + n_bands + C)
+    T = 50003  # odd length: ragged last chunk + scalar epilogue; split in time (warm-up launch)
+    x = (0.1 * rng.standard_normal((C, T))).astype(np.float32)
+    mk = lambda: [fx.filter.BiquadBPF(150.0 * (1.12 ** i), 1.414, 48000) for i in range(n_bands)]
+    filters = mk()
+    bank = SosBank(filters, mode="stack")
+    before = _native.kernel_launches()
+    y = bank(torch.from_numpy(x).to(DEV)).cpu().numpy()
+    assert _native.kernel_launches() - before <= 2 * ((n_bands + 31) // 32)
+    sos = np.stack([f._sos.numpy() for f in filters])
+    want = oracle.filterbank_stack(x, sos)
+    assert y.shape == want.shape == (n_bands, C, T)
+    assert max(rel_to_max(y[b], want[b]) for b in range(n_bands)) < TOL
+    for flags in (_native.TFX_NO_TILE, _native.TFX_NO_SPLIT):
+        other = SosBank(mk(), mode="stack")
+        other.flags = flags
+        y2 = other(torch.from_numpy(x).to(DEV)).cpu().numpy()
+        assert max(rel_to_max(y2[b], want[b]) for b in range(n_bands)) < TOL
+    for i in {0, n_bands // 2, n_bands - 1}:
+        _, wsx, wsy = oracle.sos_cascade(x, sos[i])
+        np.testing.assert_allclose(filters[i]._state_x.cpu().numpy(), wsx, rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(filters[i]._state_y.cpu().numpy(), wsy, rtol=1e-3, atol=1e-5 * np.abs(wsy).max())
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64", "auto"])
+def test_stack_tile_multi_section_chunked(precision):
+    """Bands of different orders (padded to Kb = 3), fed in uneven chunks incl. a 1-sample one: outputs and
+    carried state match the children run alone (reference filterbank.py:183-185 + iir.py state contract)."""
+    from torchfx_b200 import _ops
+    from torchfx_b200.filter._sosbank import SosBank
+
+    rng = np.random.default_rng(2024)
+    x = (0.1 * rng.standard_normal((64, 120000))).astype(np.float32)
+
+    def make():
+        return [fx.filter.LoButterworth(3000, order=4, fs=48000), fx.filter.HiButterworth(60, order=6, fs=48000),
+                fx.filter.BiquadBPF(30, 1.414, 48000), fx.filter.ParametricEQ(1000, 2.0, 3.0, fs=48000),
+                fx.filter.BiquadNotch(50, 5.0, 48000)]
+
+    filters = make()
+    bank = SosBank(filters, mode="stack")
+    xt = torch.from_numpy(x).to(DEV)
+    old = _ops.get_default_precision()
+    _ops.set_default_precision(precision)
+    try:
+        y = torch.cat([bank(xt[:, :1]), bank(xt[:, 1:2]), bank(xt[:, 2:70001]), bank(xt[:, 70001:])], dim=2).cpu().numpy()
+    finally:
+        _ops.set_default_precision(old)
+    tol = 5e-3 if precision == "f32" else TOL  # 30 Hz / 50 Hz / 60 Hz sections are float32-hostile
+    for i, f in enumerate(make()):
+        f.compute_coefficients()
+        want, wsx, wsy = oracle.sos_cascade(x, f._sos.numpy())
+        assert rel_to_max(y[i], want) < tol, (i, precision)
+        if precision != "f32":
+            np.testing.assert_allclose(filters[i]._state_x.cpu().numpy(), wsx, rtol=1e-5, atol=1e-6 * max(1.0, np.abs(wsx).max()))
+
+
+def test_stack_tile_config5_shape_properties():
+    """Config 5 (LogFilterBank(32) x 256 ch) at a length the oracle cannot cover in seconds: linearity of the
+    whole bank plus oracle parity on 3 channels; exactly 2 launches."""
+    C, T = 256, 960000
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x1 = 0.1 * torch.randn(C, T, device=DEV, generator=g)
+    x2 = 0.1 * torch.randn(C, T, device=DEV, generator=g)
+    bank = fx.filter.LogFilterBank(n_bands=32, f_min=20.0, f_max=20000.0, fs=48000)
+    def run(x):
+        bank.reset_state()
+        return bank(x)
+    before = _native.kernel_launches()
+    y1 = run(x1)
+    assert _native.kernel_launches() - before == 2
+    y12 = run(0.5 * x1 + x2)
+    y12 -= 0.5 * y1
+    y12 -= run(x2)
+    err = (y12.abs().amax(dim=(1, 2)) / y1.abs().amax(dim=(1, 2))).max().item()
+    assert err < 5e-6
+    sel = [0, 100, 255]
+    bank.compute_coefficients()
+    want = oracle.filterbank_stack(x1[sel].cpu().numpy(), np.stack([f._sos.numpy() for f in bank.filters]))
+    got = y1[:, sel].cpu().numpy()
+    assert max(rel_to_max(got[b], want[b]) for b in range(32)) < TOL

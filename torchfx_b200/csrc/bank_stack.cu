@@ -1,0 +1,445 @@
+// bank_stack.cu -- STACK filterbank (LogFilterBank, filter/filterbank.py:183-185: n_bands native
+// calls + torch.stack) with lanes = channels.
+//
+// A CTA of W warps owns 32 CONSECUTIVE CHANNELS over one time segment.  The [32 ch x 64 samples]
+// input tile is fetched ONCE per CTA (cp.async.cg, 128-byte XOR swizzle, two stages) and every
+// warp filters it with "its" bands (band b belongs to warp b mod W): lane r runs the DF2T
+// recurrence of band b over row r into the warp's private output tile, which then leaves the
+// SM as 32 coalesced 256-byte rows of y[b, c0 .. c0+31, n .. n+63] (streaming 16-byte stores).
+// So x costs 4/N bytes per lane-sample and y 4 bytes: the algorithmic 4*(1+1/N).
+//
+// Why not band-per-lane (bank_stream_kernel, filterbank.cu, still used for few channels and
+// float64 I/O): with lanes = channels the band loop is warp-uniform, so
+//   * precision is decided PER BAND (bit b of f64_mask): a 20 Hz band that needs the float64
+//     recurrence no longer drags the 10 kHz bands onto the FP64 pipe;
+//   * the warm-up launch (segment start states) runs each band only over ITS OWN decay length
+//     (warm_b): in a log-spaced bank the sum of the decay lengths is ~5x the longest one, not Nx;
+//   * band states live in shared memory between tiles ([slot][section][lane] double2, 2 LDS + 2 STS
+//     per band per 64 samples) and coefficients come from the constant bank, so registers do not
+//     limit the number of bands and all control flow and addressing is warp-uniform.
+// DF1 state contract ([N, Kb, C, 2] float64, in place), time segmentation and warm-up launch are
+// those of the other kernels (sos_plan.cpp); the last two samples of a channel run through a
+// scalar epilogue that records each section's DF1 history.
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
+#include "bank_tile.h"
+#include "common.cuh"
+#include "stream_common.cuh"
+
+namespace tfx {
+namespace {
+
+constexpr int kMaxWarps = 8;
+constexpr int kStagesX = 2;
+constexpr int kTileBytes = 32 * 256;
+constexpr int kCH = 64;  // samples per chunk (float32 I/O)
+constexpr int kMaxCtas = 8;
+
+template <int KB>
+struct StackCoef {
+    double b0[32][KB], b1[32][KB], b2[32][KB], a1[32][KB], a2[32][KB];
+};
+
+struct StackGeom {
+    const float *x;
+    float *y;
+    int64_t ldx, ldy, ldb, C, T;
+    int64_t S, Lseg, warm;  // warm > 0: this launch is the warm-up pass (warm = longest band warm-up)
+    double *ws;             // [(b * KB + k) * 2 + h][C * S] segment start states (DF2T, double)
+    int64_t ws_stride;
+    double *state_x;  // [N, KB, C, 2]
+    double *state_y;
+    int n_bands;        // bands in this launch (<= 32)
+    int W;              // warps per CTA
+    int bpw;            // band slots per warp = ceil(n_bands / W)
+    uint32_t f64_mask;  // bit b: band b runs the float64 recurrence
+    int vec_ok;
+    int band_id[32];  // global band index of local band b (y plane and state block)
+    int warm_b[32];   // warm-up samples band b needs (multiple of 64, <= warm)
+};
+
+__host__ __device__ constexpr int warp_bytes(int bpw, int KB) { return kTileBytes + bpw * KB * 512; }
+__host__ __device__ constexpr int cta_bytes(int W, int bpw, int KB) { return 128 + kStagesX * kTileBytes + W * warp_bytes(bpw, KB); }
+
+// byte offset of the 16-byte column v (0..15) of row r inside a swizzled tile (as sos_tile.cuh)
+__device__ __forceinline__ int col_offset(int r, int v) { return (v >> 3) * 4096 + r * 128 + (((v & 7) ^ (r & 7)) << 4); }
+__device__ __forceinline__ int elem_offset(int r, int e) { return col_offset(r, e >> 2) + (e & 3) * 4; }
+
+// One band over one chunk of my row: state in and out of shared memory.
+template <typename CT, int KB, bool WRITE>
+__device__ __forceinline__ void band_chunk(const StackCoef<KB> &cd, int b, const unsigned char *xin, unsigned char *out, double2 *st,
+                                           int lane, int cnt) {
+    CT b0[KB], b1[KB], b2[KB], na1[KB], na2[KB], s1[KB], s2[KB];
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+        b0[k] = static_cast<CT>(cd.b0[b][k]);
+        b1[k] = static_cast<CT>(cd.b1[b][k]);
+        b2[k] = static_cast<CT>(cd.b2[b][k]);
+        na1[k] = static_cast<CT>(-cd.a1[b][k]);
+        na2[k] = static_cast<CT>(-cd.a2[b][k]);
+        const double2 s = st[k * 32 + lane];
+        s1[k] = static_cast<CT>(s.x);
+        s2[k] = static_cast<CT>(s.y);
+    }
+    auto step = [&](float x) -> float {
+        CT v = static_cast<CT>(x);
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            const CT y = fma_rn(b0[k], v, s1[k]);
+            s1[k] = fma_rn(na1[k], y, fma_rn(b1[k], v, s2[k]));
+            s2[k] = fma_rn(na2[k], y, b2[k] * v);
+            v = y;
+        }
+        return static_cast<float>(v);
+    };
+    if (cnt == kCH) {
+#pragma unroll 4
+        for (int v = 0; v < 16; ++v) {
+            float4 a = *reinterpret_cast<const float4 *>(xin + col_offset(lane, v));
+            a.x = step(a.x);
+            a.y = step(a.y);
+            a.z = step(a.z);
+            a.w = step(a.w);
+            if (WRITE) *reinterpret_cast<float4 *>(out + col_offset(lane, v)) = a;
+        }
+    } else {
+        for (int e = 0; e < cnt; ++e) {
+            const float y = step(*reinterpret_cast<const float *>(xin + elem_offset(lane, e)));
+            if (WRITE) *reinterpret_cast<float *>(out + elem_offset(lane, e)) = y;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KB; ++k) st[k * 32 + lane] = make_double2(static_cast<double>(s1[k]), static_cast<double>(s2[k]));
+}
+
+// The last `tail` (<= 2) samples of my channel for one band, straight from / to global memory,
+// recording every section's input / output: that IS the DF1 state handed back.
+template <typename CT, int KB>
+__device__ __forceinline__ void band_tail(const StackCoef<KB> &cd, const StackGeom &g, int b, int64_t gb, int64_t c, int64_t n1, int tail,
+                                          bool from_true_state, const double2 *st, int lane) {
+    CT s1[KB], s2[KB], hx[KB][2], hy[KB][2];
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+        const double2 s = st[k * 32 + lane];
+        s1[k] = static_cast<CT>(s.x);
+        s2[k] = static_cast<CT>(s.y);
+        const int64_t o = ((gb * KB + k) * g.C + c) * 2;
+        hx[k][0] = hx[k][1] = hy[k][0] = hy[k][1] = CT(0);
+        if (from_true_state) {  // consulted only when fewer than two samples are filtered (then S == 1)
+            hx[k][0] = static_cast<CT>(g.state_x[o]);
+            hx[k][1] = static_cast<CT>(g.state_x[o + 1]);
+            hy[k][0] = static_cast<CT>(g.state_y[o]);
+            hy[k][1] = static_cast<CT>(g.state_y[o + 1]);
+        }
+    }
+    for (int e = 0; e < tail; ++e) {
+        const int64_t n = n1 - tail + e;
+        CT v = static_cast<CT>(g.x[c * g.ldx + n]);
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            const CT bb0 = static_cast<CT>(cd.b0[b][k]), bb1 = static_cast<CT>(cd.b1[b][k]), bb2 = static_cast<CT>(cd.b2[b][k]);
+            const CT na1 = static_cast<CT>(-cd.a1[b][k]), na2 = static_cast<CT>(-cd.a2[b][k]);
+            const CT y = fma_rn(bb0, v, s1[k]);
+            s1[k] = fma_rn(na1, y, fma_rn(bb1, v, s2[k]));
+            s2[k] = fma_rn(na2, y, bb2 * v);
+            hx[k][1] = hx[k][0];
+            hx[k][0] = v;
+            hy[k][1] = hy[k][0];
+            hy[k][0] = y;
+            v = y;
+        }
+        g.y[gb * g.ldb + c * g.ldy + n] = static_cast<float>(v);
+    }
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+        const int64_t o = ((gb * KB + k) * g.C + c) * 2;
+        g.state_x[o] = static_cast<double>(hx[k][0]);
+        g.state_x[o + 1] = static_cast<double>(hx[k][1]);
+        g.state_y[o] = static_cast<double>(hy[k][0]);
+        g.state_y[o + 1] = static_cast<double>(hy[k][1]);
+    }
+}
+
+template <int KB>
+__global__ void __launch_bounds__(kMaxWarps * 32, 2)
+bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constant__ StackGeom g) {
+    extern __shared__ unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int nthreads = g.W * 32;
+    unsigned char *base_sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    unsigned char *xring = base_sm;
+    unsigned char *otile = base_sm + kStagesX * kTileBytes + warp * warp_bytes(g.bpw, KB);
+    double2 *stsm = reinterpret_cast<double2 *>(otile + kTileBytes);  // [slot * KB + k][lane]
+
+    // ---- the item: channel group x time segment (CTA-uniform) -----------------------------------
+    const bool warm_pass = g.warm > 0;
+    const int64_t item = blockIdx.x;
+    int64_t grp, j, n0, n1;
+    if (warm_pass) {
+        const int64_t sm1 = g.S - 1;
+        grp = item / sm1;
+        j = item - grp * sm1 + 1;
+        n1 = j * g.Lseg;
+        n0 = max(n1 - g.warm, static_cast<int64_t>(0));
+    } else {
+        grp = item / g.S;
+        j = item - grp * g.S;
+        n0 = j * g.Lseg;
+        n1 = min(g.T, n0 + g.Lseg);
+    }
+    const int64_t c0 = grp * 32;
+    const int nrows = static_cast<int>(min(static_cast<int64_t>(32), g.C - c0));
+    const int64_t c = c0 + lane;
+    const bool live = lane < nrows;
+    const bool do_tail = !warm_pass && (j == g.S - 1) && g.state_x != nullptr;
+    const int tail = do_tail ? static_cast<int>(min(static_cast<int64_t>(2), n1 - n0)) : 0;
+    const int64_t len = n1 - n0 - tail;
+    const int64_t nch = (len + kCH - 1) / kCH;
+
+    // ---- start states of my bands -> shared memory ------------------------------------------------
+    for (int slot = 0; slot < g.bpw; ++slot) {
+        const int b = warp + slot * g.W;
+        if (b >= g.n_bands) break;
+        const int64_t gb = g.band_id[b];
+        // absolute sample at which band b starts in this launch: the segment start, or (warm-up) its own window
+        const int64_t start_b = warm_pass ? max(n1 - static_cast<int64_t>(g.warm_b[b]), static_cast<int64_t>(0)) : n0;
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            double a = 0.0, d = 0.0;
+            if (live) {
+                if (start_b == 0) {
+                    if (g.state_x != nullptr) {
+                        const int64_t o = ((gb * KB + k) * g.C + c) * 2;
+                        const double x1 = g.state_x[o], x2 = g.state_x[o + 1];
+                        const double y1 = g.state_y[o], y2 = g.state_y[o + 1];
+                        a = cd.b1[b][k] * x1 + cd.b2[b][k] * x2 - cd.a1[b][k] * y1 - cd.a2[b][k] * y2;
+                        d = cd.b2[b][k] * x1 - cd.a2[b][k] * y1;
+                    }
+                } else if (!warm_pass) {
+                    const double *wsp = g.ws + (c * g.S + j);
+                    a = wsp[((b * KB + k) * 2) * g.ws_stride];
+                    d = wsp[((b * KB + k) * 2 + 1) * g.ws_stride];
+                }
+            }
+            stsm[(slot * KB + k) * 32 + lane] = make_double2(a, d);
+        }
+    }
+
+    auto issue_load = [&](int64_t i, int stage) {
+        unsigned char *tile = xring + stage * kTileBytes;
+        const int64_t base = i * kCH;
+        const int cnt = static_cast<int>(min(len - base, static_cast<int64_t>(kCH)));
+        if (cnt == kCH && g.vec_ok) {
+            for (int idx = tid; idx < 32 * 16; idx += nthreads) {
+                const int r = idx >> 4, piece = idx & 15;
+                if (r < nrows) cp_async<16>(tile + col_offset(r, piece), g.x + (c0 + r) * g.ldx + n0 + base + piece * 4);
+            }
+        } else {
+            for (int idx = tid; idx < 32 * kCH; idx += nthreads) {
+                const int r = idx >> 6, e = idx & 63;
+                if (r < nrows && e < cnt) cp_async<4>(tile + elem_offset(r, e), g.x + (c0 + r) * g.ldx + n0 + base + e);
+            }
+        }
+    };
+
+#pragma unroll
+    for (int st = 0; st < kStagesX; ++st) {
+        if (st < nch) issue_load(st, st);
+        cp_async_commit();
+    }
+
+    const int piece = lane & 15;
+    const int half = lane >> 4;
+    int stage = 0;
+    for (int64_t i = 0; i < nch; ++i) {
+        cp_async_wait<kStagesX - 1>();
+        __syncthreads();  // everyone's share of tile i has landed (also orders the state init above)
+        const unsigned char *tile = xring + stage * kTileBytes;
+        const int64_t base = i * kCH;
+        const int cnt = static_cast<int>(min(len - base, static_cast<int64_t>(kCH)));
+
+        for (int slot = 0; slot < g.bpw; ++slot) {
+            const int b = warp + slot * g.W;
+            if (b >= g.n_bands) break;
+            double2 *st = stsm + slot * KB * 32;
+            const bool is64 = (g.f64_mask >> b) & 1u;
+            if (warm_pass) {
+                const int64_t start_b = max(n1 - static_cast<int64_t>(g.warm_b[b]), static_cast<int64_t>(0));
+                if (n0 + base < start_b) continue;  // this band's window has not begun yet
+                if (live) {
+                    if (is64)
+                        band_chunk<double, KB, false>(cd, b, tile, nullptr, st, lane, cnt);
+                    else
+                        band_chunk<float, KB, false>(cd, b, tile, nullptr, st, lane, cnt);
+                }
+                continue;
+            }
+            if (live) {
+                if (is64)
+                    band_chunk<double, KB, true>(cd, b, tile, otile, st, lane, cnt);
+                else
+                    band_chunk<float, KB, true>(cd, b, tile, otile, st, lane, cnt);
+            }
+            __syncwarp();
+            // ---- the band's [32 x 64] tile leaves as coalesced rows of y[gb] ---------------------
+            float *yb = g.y + static_cast<int64_t>(g.band_id[b]) * g.ldb + n0 + base;
+            if (cnt == kCH && g.vec_ok) {
+                float *yrow = yb + (c0 + half) * g.ldy + piece * 4;
+                const int64_t ldy2 = 2 * g.ldy;
+                if (nrows == 32) {
+#pragma unroll
+                    for (int t = 0; t < 16; ++t)
+                        st_stream16(yrow + t * ldy2, *reinterpret_cast<const float4 *>(otile + col_offset(2 * t + half, piece)));
+                } else {
+#pragma unroll 1
+                    for (int t = 0; t < 16; ++t)
+                        if (2 * t + half < nrows)
+                            st_stream16(yrow + t * ldy2, *reinterpret_cast<const float4 *>(otile + col_offset(2 * t + half, piece)));
+                }
+            } else {
+#pragma unroll 1
+                for (int r = 0; r < nrows; ++r) {
+                    float *dst = yb + (c0 + r) * g.ldy;
+                    for (int e = lane; e < cnt; e += 32) dst[e] = *reinterpret_cast<const float *>(otile + elem_offset(r, e));
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();  // tile i is free: refill its stage
+        if (i + kStagesX < nch) issue_load(i + kStagesX, stage);
+        cp_async_commit();
+        stage = (stage + 1 == kStagesX) ? 0 : stage + 1;
+    }
+    cp_async_wait<0>();
+
+    if (!live) return;
+    if (warm_pass) {
+        for (int slot = 0; slot < g.bpw; ++slot) {
+            const int b = warp + slot * g.W;
+            if (b >= g.n_bands) break;
+            double *wsp = g.ws + (c * g.S + j);
+#pragma unroll
+            for (int k = 0; k < KB; ++k) {
+                const double2 s = stsm[(slot * KB + k) * 32 + lane];
+                wsp[((b * KB + k) * 2) * g.ws_stride] = s.x;
+                wsp[((b * KB + k) * 2 + 1) * g.ws_stride] = s.y;
+            }
+        }
+        return;
+    }
+    if (do_tail) {
+        const bool from_true_state = n0 == 0;
+        for (int slot = 0; slot < g.bpw; ++slot) {
+            const int b = warp + slot * g.W;
+            if (b >= g.n_bands) break;
+            const double2 *st = stsm + slot * KB * 32;
+            if ((g.f64_mask >> b) & 1u)
+                band_tail<double, KB>(cd, g, b, g.band_id[b], c, n1, tail, from_true_state, st, lane);
+            else
+                band_tail<float, KB>(cd, g, b, g.band_id[b], c, n1, tail, from_true_state, st, lane);
+        }
+    }
+}
+
+int ctas_per_sm(int W, int bpw, int KB) {
+    const int n = kSmemPerSm / (cta_bytes(W, bpw, KB) + 1024);
+    const int by_threads = 2048 / (W * 32);
+    return std::max(1, std::min(std::min(n, by_threads), kMaxCtas));
+}
+
+template <int KB>
+int launch_stack_kb(const SosSection *sec, StackGeom g, const Segmentation &seg, cudaStream_t stream) {
+    StackCoef<KB> cd;
+    for (int b = 0; b < 32; ++b)
+        for (int k = 0; k < KB; ++k) {
+            const SosSection id{1.0, 0.0, 0.0, 0.0, 0.0};
+            const SosSection &s = b < g.n_bands ? sec[b * KB + k] : id;
+            cd.b0[b][k] = s.b0;
+            cd.b1[b][k] = s.b1;
+            cd.b2[b][k] = s.b2;
+            cd.a1[b][k] = s.a1;
+            cd.a2[b][k] = s.a2;
+        }
+    auto kern = bank_stack_kernel<KB>;
+    TFX_ENSURE_SMEM(kern, cta_bytes(kMaxWarps, 32 / kMaxWarps, KB));
+    const int smem = cta_bytes(g.W, g.bpw, KB);
+    const int64_t G = (g.C + 31) / 32;
+    if (seg.S > 1) {
+        StackGeom gw = g;
+        gw.warm = seg.warm;
+        kern<<<static_cast<unsigned>(G * (seg.S - 1)), g.W * 32, smem, stream>>>(cd, gw);
+        TFX_CHECK_LAUNCH("bank_stack_kernel(warm-up)");
+    }
+    g.warm = 0;
+    kern<<<static_cast<unsigned>(G * seg.S), g.W * 32, smem, stream>>>(cd, g);
+    TFX_CHECK_LAUNCH("bank_stack_kernel");
+    return TFX_OK;
+}
+
+}  // namespace
+
+bool bank_stack_tile_ok(int N, int Kb, int64_t C) {
+    const int64_t G = (C + 31) / 32;
+    return N >= 1 && Kb >= 1 && Kb <= 4 && C * 5 >= G * 32 * 4 && G * 64 < (int64_t(1) << 31);
+}
+
+int launch_bank_stack(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, int64_t ldb, const SosSection *sec,
+                      const int *band_id, const int64_t *warm_b, uint32_t f64_mask, int nb, int Kb, bool no_split, void *workspace,
+                      size_t workspace_bytes, double *state_x, double *state_y, cudaStream_t stream) {
+    StackGeom g{};
+    g.x = x;
+    g.y = y;
+    g.ldx = ldx;
+    g.ldy = ldy;
+    g.ldb = ldb;
+    g.C = C;
+    g.T = T;
+    g.n_bands = nb;
+    g.W = std::min(kMaxWarps, nb);
+    g.bpw = (nb + g.W - 1) / g.W;
+    g.f64_mask = f64_mask;
+    g.state_x = state_x;
+    g.state_y = state_y;
+    int64_t warm_max = 0;
+    for (int b = 0; b < 32; ++b) {
+        g.band_id[b] = band_id[b < nb ? b : 0];
+        const int64_t w = b < nb ? warm_b[b] : 0;
+        if (w < 0) no_split = true;
+        const int64_t wa = w < 0 ? 0 : (w + 63) / 64 * 64;
+        g.warm_b[b] = static_cast<int>(std::min<int64_t>(wa, int64_t(1) << 30));
+        warm_max = std::max(warm_max, wa);
+    }
+    if (warm_max > (int64_t(1) << 30)) no_split = true;
+    const int64_t lanes = (C + 31) / 32 * 32;
+    const int64_t capacity = static_cast<int64_t>(sm_count()) * ctas_per_sm(g.W, g.bpw, Kb) * 32;
+    const Segmentation seg = choose_segmentation(lanes, T, warm_max, capacity, no_split);
+    g.S = seg.S;
+    g.Lseg = seg.Lseg;
+    g.ws = static_cast<double *>(workspace);
+    g.ws_stride = C * seg.S;
+    if (seg.S > 1) {
+        const size_t need = static_cast<size_t>(2 * Kb * nb) * static_cast<size_t>(C * seg.S) * 8;
+        if (workspace == nullptr || workspace_bytes < need) {
+            set_error("filterbank: workspace of %zu bytes needed, %zu given (query tfx_filterbank_workspace_bytes)", need, workspace_bytes);
+            return TFX_EWORKSPACE;
+        }
+    }
+    const size_t esz = 4;
+    g.vec_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0) && ((ldx * esz) % 16 == 0) &&
+               ((ldy * esz) % 16 == 0) && ((ldb * esz) % 16 == 0);
+    switch (Kb) {
+        case 1: return launch_stack_kb<1>(sec, g, seg, stream);
+        case 2: return launch_stack_kb<2>(sec, g, seg, stream);
+        case 3: return launch_stack_kb<3>(sec, g, seg, stream);
+        case 4: return launch_stack_kb<4>(sec, g, seg, stream);
+        default: set_error("filterbank: Kb must be in [1, 4]"); return TFX_EINVAL;
+    }
+}
+
+int64_t bank_stack_max_streams() { return static_cast<int64_t>(sm_count()) * kMaxCtas * 32; }
+
+}  // namespace tfx

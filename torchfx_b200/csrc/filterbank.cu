@@ -476,6 +476,33 @@ int filterbank_device(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, int
         }
     }
 
+    // STACK banks with enough channels: lanes = channels, per-band precision and warm-up (bank_stack.cu)
+    if constexpr (sizeof(IO) == 4) {
+        if (mode == TFX_BANK_STACK && !(flags & TFX_NO_TILE) && bank_stack_tile_ok(N, Kb, C)) {
+            const uint32_t want = flags & TFX_PREC_MASK;
+            TFX_REQUIRE(want == TFX_PREC_AUTO || want == TFX_PREC_F32 || want == TFX_PREC_F64, "filterbank: bad precision flag");
+            for (int lo = 0; lo < N; lo += 32) {
+                const int nb = std::min(32, N - lo);
+                std::vector<SosSection> sec;
+                int band_id[32];
+                int64_t warm_b[32];
+                uint32_t mask = 0;
+                for (int b = 0; b < nb; ++b) {
+                    const SosPlan &pl = *plans[lo + b];
+                    const uint32_t pb = want == TFX_PREC_AUTO ? static_cast<uint32_t>(pl.auto_prec) : want;
+                    if (pb == TFX_PREC_F64) mask |= 1u << b;
+                    warm_b[b] = pb == TFX_PREC_F32 ? pl.passes[0].warm_f32 : pl.passes[0].warm_f64_io32;
+                    band_id[b] = lo + b;
+                    for (int k = 0; k < Kb; ++k) sec.push_back(pl.sec[k]);
+                }
+                rc = launch_bank_stack(x, y, C, T, ldx, ldy, ldb, sec.data(), band_id, warm_b, mask, nb, Kb, (flags & TFX_NO_SPLIT) != 0,
+                                       workspace, workspace_bytes, state_x, state_y, static_cast<cudaStream_t>(stream_v));
+                if (rc != TFX_OK) return rc;
+            }
+            return TFX_OK;
+        }
+    }
+
     // Precision per band.  With TFX_PREC_AUTO the bank is split by the per-band probe: bands whose
     // float32 recurrence is accurate run in a float32 launch, the others (low corners) in a
     // float64 launch -- the lanes of one launch execute one instruction stream, so mixing would
@@ -583,7 +610,8 @@ size_t tfx_filterbank_workspace_bytes(int64_t C, int64_t T, int N, int Kb) {
     // channel-tile SUM path (bank_tile.cu): up to 8 sections, kOversub work items per resident warp
     const int64_t tile_streams = tfx::bank_tile_stream_capacity() * tfx::kOversub + C + 128;
     const size_t tile_path = tfx::bank_sum_tile_ok(N, Kb, C) ? tfx::kWsHeader + static_cast<size_t>(2 * N * Kb) * static_cast<size_t>(tile_streams) * 8 + 256 : 0;
-    return std::max(stream_path, tile_path);
+    const size_t stack_path = static_cast<size_t>(2 * Kb * nb) * static_cast<size_t>(tfx::bank_stack_max_streams() + C + 128) * 8 + 256;
+    return std::max(std::max(stream_path, tile_path), stack_path);
 }
 
 int tfx_filterbank_f32(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, int64_t ldb,
