@@ -31,11 +31,23 @@
 namespace tfx {
 namespace {
 
-constexpr int kMaxWarps = 8;
+#ifndef TFX_BS_WARPS
+#define TFX_BS_WARPS 8
+#endif
+#ifndef TFX_BS_CH
+#define TFX_BS_CH 64
+#endif
+#ifndef TFX_BS_STORE
+#define TFX_BS_STORE 0
+#endif
+constexpr int kMaxWarps = TFX_BS_WARPS;
 constexpr int kStagesX = 2;
-constexpr int kTileBytes = 32 * 256;
-constexpr int kCH = 64;  // samples per chunk (float32 I/O)
+constexpr int kCH = TFX_BS_CH;  // samples per chunk (float32 I/O): rows of 256 or 512 bytes
+constexpr int kNV = kCH / 4;    // 16-byte pieces per row
+constexpr int kTileBytes = 32 * kCH * 4;
 constexpr int kMaxCtas = 8;
+static_assert(kCH == 64 || kCH == 128, "tile rows are 256 or 512 bytes");
+static_assert(32 % kMaxWarps == 0, "warps per CTA must divide 32");
 
 template <int KB>
 struct StackCoef {
@@ -61,10 +73,18 @@ struct StackGeom {
 };
 
 __host__ __device__ constexpr int warp_bytes(int bpw, int KB) { return kTileBytes + bpw * KB * 512; }
-__host__ __device__ constexpr int cta_bytes(int W, int bpw, int KB) { return 128 + kStagesX * kTileBytes + W * warp_bytes(bpw, KB); }
+// input ring (float32) + one float64 copy of the current input tile + per-warp output tile and band states
+__host__ __device__ constexpr int cta_bytes(int W, int bpw, int KB) { return (kStagesX + 2) * kTileBytes + W * warp_bytes(bpw, KB); }
 
 // byte offset of the 16-byte column v (0..15) of row r inside a swizzled tile (as sos_tile.cuh)
 __device__ __forceinline__ int col_offset(int r, int v) { return (v >> 3) * 4096 + r * 128 + (((v & 7) ^ (r & 7)) << 4); }
+__device__ __forceinline__ void store_row16(float *gptr, const float4 &v) {
+#if TFX_BS_STORE == 0
+    st_stream16(gptr, v);
+#else
+    *reinterpret_cast<float4 *>(gptr) = v;
+#endif
+}
 __device__ __forceinline__ int elem_offset(int r, int e) { return col_offset(r, e >> 2) + (e & 3) * 4; }
 
 // One band over one chunk of my row: state in and out of shared memory.
@@ -95,14 +115,17 @@ __device__ __forceinline__ void band_chunk(const StackCoef<KB> &cd, int b, const
         return static_cast<float>(v);
     };
     if (cnt == kCH) {
+        float4 a = *reinterpret_cast<const float4 *>(xin + col_offset(lane, 0));
 #pragma unroll 4
-        for (int v = 0; v < 16; ++v) {
-            float4 a = *reinterpret_cast<const float4 *>(xin + col_offset(lane, v));
+        for (int v = 0; v < kNV; ++v) {
+            // next vector first: the compiler cannot hoist a load over the store into the output tile
+            const float4 nxt = *reinterpret_cast<const float4 *>(xin + col_offset(lane, (v + 1) & (kNV - 1)));
             a.x = step(a.x);
             a.y = step(a.y);
             a.z = step(a.z);
             a.w = step(a.w);
             if (WRITE) *reinterpret_cast<float4 *>(out + col_offset(lane, v)) = a;
+            a = nxt;
         }
     } else {
         for (int e = 0; e < cnt; ++e) {
@@ -112,6 +135,58 @@ __device__ __forceinline__ void band_chunk(const StackCoef<KB> &cd, int b, const
     }
 #pragma unroll
     for (int k = 0; k < KB; ++k) st[k * 32 + lane] = make_double2(static_cast<double>(s1[k]), static_cast<double>(s2[k]));
+}
+
+// Float64 band: reads the CTA's float64 copy of the input tile (converted ONCE per tile, not once
+// per band -- F2F runs at 16 lanes/clk/SM, so a per-band conversion costs the FP64 pipe more than
+// the band's five DFMAs), rounds only the output.
+template <int KB, bool WRITE>
+__device__ __forceinline__ void band_chunk64(const StackCoef<KB> &cd, int b, const unsigned char *x64, unsigned char *out, double2 *st,
+                                             int lane, int cnt) {
+    double b0[KB], b1[KB], b2[KB], na1[KB], na2[KB], s1[KB], s2[KB];
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+        b0[k] = cd.b0[b][k];
+        b1[k] = cd.b1[b][k];
+        b2[k] = cd.b2[b][k];
+        na1[k] = -cd.a1[b][k];
+        na2[k] = -cd.a2[b][k];
+        const double2 s = st[k * 32 + lane];
+        s1[k] = s.x;
+        s2[k] = s.y;
+    }
+    auto step = [&](double v) -> float {
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            const double y = __fma_rn(b0[k], v, s1[k]);
+            s1[k] = __fma_rn(na1[k], y, __fma_rn(b1[k], v, s2[k]));
+            s2[k] = __fma_rn(na2[k], y, b2[k] * v);
+            v = y;
+        }
+        return static_cast<float>(v);
+    };
+    if (cnt == kCH) {
+        double2 a = *reinterpret_cast<const double2 *>(x64 + col_offset(lane, 0));
+#pragma unroll 4
+        for (int v = 0; v < kNV; ++v) {
+            const double2 c = *reinterpret_cast<const double2 *>(x64 + col_offset(lane, 2 * v + 1));
+            const double2 nxt = *reinterpret_cast<const double2 *>(x64 + col_offset(lane, (2 * v + 2) & (2 * kNV - 1)));
+            float4 o;
+            o.x = step(a.x);
+            o.y = step(a.y);
+            o.z = step(c.x);
+            o.w = step(c.y);
+            if (WRITE) *reinterpret_cast<float4 *>(out + col_offset(lane, v)) = o;
+            a = nxt;
+        }
+    } else {
+        for (int e = 0; e < cnt; ++e) {
+            const float y = step(*reinterpret_cast<const double *>(x64 + col_offset(lane, e >> 1) + (e & 1) * 8));
+            if (WRITE) *reinterpret_cast<float *>(out + elem_offset(lane, e)) = y;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KB; ++k) st[k * 32 + lane] = make_double2(s1[k], s2[k]);
 }
 
 // The last `tail` (<= 2) samples of my channel for one band, straight from / to global memory,
@@ -165,14 +240,17 @@ __device__ __forceinline__ void band_tail(const StackCoef<KB> &cd, const StackGe
 template <int KB>
 __global__ void __launch_bounds__(kMaxWarps * 32, 2)
 bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constant__ StackGeom g) {
-    extern __shared__ unsigned char smem_raw[];
+    // plain pointer arithmetic on the __shared__ array keeps the address space: LDS / STS, not generic LD / ST
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int nthreads = g.W * 32;
-    unsigned char *base_sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    unsigned char *base_sm = smem_raw;
+    if ((smem_u32(smem_raw) & 127u) != 0u) __trap();  // the swizzle needs 128-byte aligned tiles
     unsigned char *xring = base_sm;
-    unsigned char *otile = base_sm + kStagesX * kTileBytes + warp * warp_bytes(g.bpw, KB);
+    unsigned char *x64 = base_sm + kStagesX * kTileBytes;  // [32 x kCH] float64, same swizzle (2 * kNV columns)
+    unsigned char *otile = base_sm + (kStagesX + 2) * kTileBytes + warp * warp_bytes(g.bpw, KB);
     double2 *stsm = reinterpret_cast<double2 *>(otile + kTileBytes);  // [slot * KB + k][lane]
 
     // ---- the item: channel group x time segment (CTA-uniform) -----------------------------------
@@ -234,13 +312,13 @@ bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constan
         const int64_t base = i * kCH;
         const int cnt = static_cast<int>(min(len - base, static_cast<int64_t>(kCH)));
         if (cnt == kCH && g.vec_ok) {
-            for (int idx = tid; idx < 32 * 16; idx += nthreads) {
-                const int r = idx >> 4, piece = idx & 15;
+            for (int idx = tid; idx < 32 * kNV; idx += nthreads) {
+                const int r = idx / kNV, piece = idx % kNV;
                 if (r < nrows) cp_async<16>(tile + col_offset(r, piece), g.x + (c0 + r) * g.ldx + n0 + base + piece * 4);
             }
         } else {
             for (int idx = tid; idx < 32 * kCH; idx += nthreads) {
-                const int r = idx >> 6, e = idx & 63;
+                const int r = idx / kCH, e = idx % kCH;
                 if (r < nrows && e < cnt) cp_async<4>(tile + elem_offset(r, e), g.x + (c0 + r) * g.ldx + n0 + base + e);
             }
         }
@@ -252,8 +330,9 @@ bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constan
         cp_async_commit();
     }
 
-    const int piece = lane & 15;
-    const int half = lane >> 4;
+    constexpr int RPI = 32 / kNV;  // rows per cooperative store instruction
+    const int piece = lane % kNV;
+    const int half = lane / kNV;
     int stage = 0;
     for (int64_t i = 0; i < nch; ++i) {
         cp_async_wait<kStagesX - 1>();
@@ -261,6 +340,16 @@ bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constan
         const unsigned char *tile = xring + stage * kTileBytes;
         const int64_t base = i * kCH;
         const int cnt = static_cast<int>(min(len - base, static_cast<int64_t>(kCH)));
+
+        if (g.f64_mask != 0u) {  // CTA-uniform: float64 copy of the tile for the float64 bands
+            for (int idx = tid; idx < 32 * kNV; idx += nthreads) {
+                const int r = idx / kNV, p = idx % kNV;
+                const float4 a = *reinterpret_cast<const float4 *>(tile + col_offset(r, p));
+                *reinterpret_cast<double2 *>(x64 + col_offset(r, 2 * p)) = make_double2(static_cast<double>(a.x), static_cast<double>(a.y));
+                *reinterpret_cast<double2 *>(x64 + col_offset(r, 2 * p + 1)) = make_double2(static_cast<double>(a.z), static_cast<double>(a.w));
+            }
+            __syncthreads();
+        }
 
         for (int slot = 0; slot < g.bpw; ++slot) {
             const int b = warp + slot * g.W;
@@ -272,7 +361,7 @@ bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constan
                 if (n0 + base < start_b) continue;  // this band's window has not begun yet
                 if (live) {
                     if (is64)
-                        band_chunk<double, KB, false>(cd, b, tile, nullptr, st, lane, cnt);
+                        band_chunk64<KB, false>(cd, b, x64, nullptr, st, lane, cnt);
                     else
                         band_chunk<float, KB, false>(cd, b, tile, nullptr, st, lane, cnt);
                 }
@@ -280,7 +369,7 @@ bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constan
             }
             if (live) {
                 if (is64)
-                    band_chunk<double, KB, true>(cd, b, tile, otile, st, lane, cnt);
+                    band_chunk64<KB, true>(cd, b, x64, otile, st, lane, cnt);
                 else
                     band_chunk<float, KB, true>(cd, b, tile, otile, st, lane, cnt);
             }
@@ -289,16 +378,16 @@ bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constan
             float *yb = g.y + static_cast<int64_t>(g.band_id[b]) * g.ldb + n0 + base;
             if (cnt == kCH && g.vec_ok) {
                 float *yrow = yb + (c0 + half) * g.ldy + piece * 4;
-                const int64_t ldy2 = 2 * g.ldy;
+                const int64_t ldy2 = RPI * g.ldy;
                 if (nrows == 32) {
-#pragma unroll
-                    for (int t = 0; t < 16; ++t)
-                        st_stream16(yrow + t * ldy2, *reinterpret_cast<const float4 *>(otile + col_offset(2 * t + half, piece)));
+#pragma unroll 16
+                    for (int t = 0; t < 32 / RPI; ++t)
+                        store_row16(yrow + t * ldy2, *reinterpret_cast<const float4 *>(otile + col_offset(RPI * t + half, piece)));
                 } else {
 #pragma unroll 1
-                    for (int t = 0; t < 16; ++t)
-                        if (2 * t + half < nrows)
-                            st_stream16(yrow + t * ldy2, *reinterpret_cast<const float4 *>(otile + col_offset(2 * t + half, piece)));
+                    for (int t = 0; t < 32 / RPI; ++t)
+                        if (RPI * t + half < nrows)
+                            store_row16(yrow + t * ldy2, *reinterpret_cast<const float4 *>(otile + col_offset(RPI * t + half, piece)));
                 }
             } else {
 #pragma unroll 1
@@ -409,7 +498,7 @@ int launch_bank_stack(const float *x, float *y, int64_t C, int64_t T, int64_t ld
         g.band_id[b] = band_id[b < nb ? b : 0];
         const int64_t w = b < nb ? warm_b[b] : 0;
         if (w < 0) no_split = true;
-        const int64_t wa = w < 0 ? 0 : (w + 63) / 64 * 64;
+        const int64_t wa = w < 0 ? 0 : (w + kCH - 1) / kCH * kCH;  // band windows start on chunk boundaries
         g.warm_b[b] = static_cast<int>(std::min<int64_t>(wa, int64_t(1) << 30));
         warm_max = std::max(warm_max, wa);
     }

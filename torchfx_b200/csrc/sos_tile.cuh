@@ -19,6 +19,9 @@ namespace {
 #ifndef TFX_T_WARPS
 #define TFX_T_WARPS 1
 #endif
+#ifndef TFX_T_PREFETCH
+#define TFX_T_PREFETCH 1
+#endif
 constexpr int kStages = TFX_T_STAGES;
 constexpr int kWarps = TFX_T_WARPS;
 constexpr int kTileBytes = 32 * 256;
@@ -245,11 +248,13 @@ sos_tile_kernel(const __grid_constant__ SosCoef<typename CtTraits<CT>::Coef, K> 
     constexpr int CH = 256 / sizeof(IO);  // samples per chunk
     constexpr int UV = K <= 2 ? 16 : (K <= 4 ? 8 : 4);
 
-    extern __shared__ unsigned char smem_raw[];
+    // Plain pointer arithmetic on the __shared__ array (no integer round trip): the compiler keeps the
+    // address space and emits LDS / STS instead of generic LD / ST for every tile access.
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    unsigned char *ring = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127)) +
-                          warp * kWarpSmem;
+    unsigned char *ring = smem_raw + warp * kWarpSmem;
+    if ((smem_u32(smem_raw) & 127u) != 0u) __trap();  // the swizzle needs 128-byte aligned tiles
     const IO *__restrict__ xg = static_cast<const IO *>(g.x);
     IO *__restrict__ yg = static_cast<IO *>(g.y);
     const bool warm_pass = g.warm > 0;
@@ -371,17 +376,26 @@ sos_tile_kernel(const __grid_constant__ SosCoef<typename CtTraits<CT>::Coef, K> 
             // ---- filter my row (channel) in place ----------------------------------------------
             if (live) {
                 if (cnt == CH && !tracked) {
+                    // the next vector is fetched before the current one is filtered and stored (the
+                    // compiler cannot hoist a load over the in-place store on its own)
+                    Vec a = *reinterpret_cast<const Vec *>(tile + col_offset(lane, 0));
 #pragma unroll UV
                     for (int v = 0; v < 16; ++v) {
-                        Vec *p = reinterpret_cast<Vec *>(tile + col_offset(lane, v));
-                        Vec a = *p;
+#if TFX_T_PREFETCH
+                        const Vec nxt = *reinterpret_cast<const Vec *>(tile + col_offset(lane, (v + 1) & 15));
+#else
+                        if (v > 0) a = *reinterpret_cast<const Vec *>(tile + col_offset(lane, v));
+#endif
                         a.x = st.step(cf, cd, g.f64_mask, a.x);
                         a.y = st.step(cf, cd, g.f64_mask, a.y);
                         if constexpr (VEC == 4) {
                             a.z = st.step(cf, cd, g.f64_mask, a.z);
                             a.w = st.step(cf, cd, g.f64_mask, a.w);
                         }
-                        *p = a;
+                        *reinterpret_cast<Vec *>(tile + col_offset(lane, v)) = a;
+#if TFX_T_PREFETCH
+                        a = nxt;
+#endif
                     }
                 } else if (!tracked) {
                     for (int e = 0; e < cnt; ++e) {

@@ -129,10 +129,12 @@ sos_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     constexpr int CH = 256 / sizeof(IO);  // samples per chunk
     constexpr int UV = K <= 2 ? 16 : (K <= 4 ? 8 : 4);
 
-    extern __shared__ unsigned char smem_raw[];
+    // plain pointer arithmetic on the __shared__ array keeps the address space: LDS / STS, not generic LD / ST
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    unsigned char *cta_base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char *cta_base = smem_raw;
+    if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
     unsigned char *ring = cta_base + warp * (kStages * kTileBytes);
     uint64_t *bars = reinterpret_cast<uint64_t *>(cta_base + kWarps * (kStages * kTileBytes) + warp * 128);
 
@@ -247,12 +249,14 @@ sos_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 
         if (live) {
             if (cnt == CH && !tracked) {
+                auto vec_at = [&](int v) { return reinterpret_cast<Vec *>(tile + (v >> 3) * 4096 + lane * 128 + (((v & 7) ^ (lane & 7)) << 4)); };
+                Vec a = *vec_at(0);
 #pragma unroll UV
                 for (int v = 0; v < 16; ++v) {
-                    Vec *p = reinterpret_cast<Vec *>(tile + (v >> 3) * 4096 + lane * 128 + (((v & 7) ^ (lane & 7)) << 4));
-                    Vec a = *p;
+                    const Vec nxt = *vec_at((v + 1) & 15);  // fetched before the in-place store below
                     filter_vec<CT, K>(cf, s1, s2, a);
-                    *p = a;
+                    *vec_at(v) = a;
+                    a = nxt;
                 }
             } else if (!tracked) {
                 for (int e = 0; e < cnt; ++e) {
