@@ -275,3 +275,43 @@ def test_stack_tile_config5_shape_properties():
     want = oracle.filterbank_stack(x1[sel].cpu().numpy(), np.stack([f._sos.numpy() for f in bank.filters]))
     got = y1[:, sel].cpu().numpy()
     assert max(rel_to_max(got[b], want[b]) for b in range(32)) < TOL
+
+
+@pytest.mark.parametrize("n,kb,n_low", [(8, 1, 3), (5, 1, 1), (3, 1, 2), (4, 2, 2), (2, 1, 1)])
+def test_sum_tile_mixed_precision_prefix(n, kb, n_low):
+    """TFX_PREC_AUTO on a bank listed by rising frequency: the float32-hostile low branches form a prefix and run
+    the float64 recurrence, the others float32 (bank_tile_mixed.cu); result within the 1e-5 bar of the float64
+    oracle, state carried over an uneven split, exactly two launches per call."""
+    from torchfx_b200.filter._sosbank import SosBank
+
+    lib = _native.load()
+    def make():
+        if kb == 1:
+            return ([fx.filter.BiquadBPF(25.0 * (1.8 ** i), 1.414, 48000) for i in range(n_low)]
+                    + [fx.filter.BiquadBPF(2500.0 * (1.35 ** i), 1.414, 48000) for i in range(n - n_low)])
+        return ([fx.filter.HiButterworth(20.0 * (1.5 ** i), order=4, fs=48000) for i in range(n_low)]
+                + [fx.filter.LoButterworth(3000.0 * (1.4 ** i), order=4, fs=48000) for i in range(n - n_low)])
+    filters = make()
+    for f in filters:
+        f.compute_coefficients()
+    import ctypes
+    precs = [lib.tfx_sos_auto_precision(f._sos.contiguous().data_ptr(), f._sos.shape[0], None) for f in filters]
+    assert precs == [_native.TFX_PREC_F64] * n_low + [_native.TFX_PREC_F32] * (n - n_low), precs
+    rng = np.random.default_rng(n * 10 + kb)
+    x = (0.1 * rng.standard_normal((64, 150001))).astype(np.float32)
+    xt = torch.from_numpy(x).to(DEV)
+    bank = SosBank(filters, mode="sum")
+    before = _native.kernel_launches()
+    y = torch.cat([bank(xt[:, :60001]), bank(xt[:, 60001:])], dim=1).cpu().numpy()
+    assert _native.kernel_launches() - before <= 4
+    sos = np.stack([f._sos.numpy() for f in filters])
+    want = oracle.filterbank_sum(x, sos)
+    assert rel_to_max(y, want) < TOL
+    # forcing float64 everywhere gives the same answer to rounding; forcing float32 does not meet the bar for these bands
+    from torchfx_b200 import _ops
+    _ops.set_default_precision("f64")
+    try:
+        y64 = SosBank(make(), mode="sum")(xt).cpu().numpy()
+    finally:
+        _ops.set_default_precision("auto")
+    assert rel_to_max(y, y64) < 2e-6

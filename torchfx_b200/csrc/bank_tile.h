@@ -17,6 +17,12 @@ template <typename CT>
 int launch_bank_sum_tile(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, const SosSection *sec, int N, int Kb,
                          const Segmentation &seg, void *ws_base, double *state_x, double *state_y, cudaStream_t stream);
 
+// Mixed precision (bank_tile_mixed.cu): branches [0, n64) on the float64 recurrence, the rest float32.
+bool bank_sum_mixed_ok(int N, int Kb, int n64);
+int launch_bank_sum_tile_mixed(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, const SosSection *sec, int N,
+                               int Kb, int n64, const Segmentation &seg, void *ws_base, double *state_x, double *state_y,
+                               cudaStream_t stream);
+
 // STACK bank with lanes = channels (bank_stack.cu): float32 I/O, <= 32 bands per launch, per-band
 // precision (bit b of f64_mask) and per-band warm-up lengths (warm_b[b] < 0: band does not decay).
 bool bank_stack_tile_ok(int N, int Kb, int64_t C);

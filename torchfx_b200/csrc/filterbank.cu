@@ -444,10 +444,17 @@ int filterbank_device(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, int
     if constexpr (sizeof(IO) == 4) {
         if (mode == TFX_BANK_SUM && !(flags & TFX_NO_TILE) && bank_sum_tile_ok(N, Kb, C)) {
             uint32_t prec = flags & TFX_PREC_MASK;
+            int n64 = 0;  // AUTO: branches [0, n64) need float64 and the others do not -> mixed kernel
             if (prec == TFX_PREC_AUTO) {
                 prec = TFX_PREC_F32;
+                bool prefix = true;
                 for (int b = 0; b < N; ++b)
-                    if (plans[b]->auto_prec == TFX_PREC_F64) prec = TFX_PREC_F64;
+                    if (plans[b]->auto_prec == TFX_PREC_F64) {
+                        prec = TFX_PREC_F64;
+                        prefix = prefix && b == n64;
+                        ++n64;
+                    }
+                if (!prefix || !bank_sum_mixed_ok(N, Kb, n64)) n64 = 0;
             }
             TFX_REQUIRE(prec == TFX_PREC_F32 || prec == TFX_PREC_F64, "filterbank: bad precision flag");
             int64_t warm_needed = 0;
@@ -470,6 +477,8 @@ int filterbank_device(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, int
                 }
             }
             cudaStream_t st = static_cast<cudaStream_t>(stream_v);
+            if (n64 > 0)
+                return launch_bank_sum_tile_mixed(x, y, C, T, ldx, ldy, sec.data(), N, Kb, n64, seg, workspace, state_x, state_y, st);
             if (prec == TFX_PREC_F32)
                 return launch_bank_sum_tile<float>(x, y, C, T, ldx, ldy, sec.data(), N, Kb, seg, workspace, state_x, state_y, st);
             return launch_bank_sum_tile<double>(x, y, C, T, ldx, ldy, sec.data(), N, Kb, seg, workspace, state_x, state_y, st);

@@ -237,6 +237,84 @@ struct Cascade<Par<CT, KB>, K> {
     }
 };
 
+// Parallel topology, mixed precision: the first N64 branches run the float64 recurrence, the others
+// float32 (TFX_PREC_AUTO when the float32-hostile branches are a prefix of the bank, the usual case of a
+// bank listed by rising frequency).  x is widened once per sample for all float64 branches; each
+// float64 branch rounds its output to float32 before the branch-ordered sum, like the reference.
+template <int N64, int KB>
+struct ParMixed {};
+template <int N64, int KB>
+struct CtTraits<ParMixed<N64, KB>> {
+    using Coef = float;
+    using Store = double;
+    static constexpr bool heavy = N64 * KB >= 4;  // register budget: mostly-float64 banks run at half the residency
+};
+template <int N64, int KB, int K>
+struct Cascade<ParMixed<N64, KB>, K> {
+    static_assert(K % KB == 0 && N64 >= 1 && N64 * KB < K, "mixed parallel bank: 1 <= N64 < branches");
+    static constexpr int K64 = N64 * KB;  // sections [0, K64) are float64
+    float f1[K], f2[K];
+    double d1[K64], d2[K64];
+    __device__ __forceinline__ void set(int k, double a, double b) {
+        f1[k] = static_cast<float>(a);
+        f2[k] = static_cast<float>(b);
+        if (k < K64) {
+            d1[k] = a;
+            d2[k] = b;
+        }
+    }
+    __device__ __forceinline__ double get1(int k) const { return k < K64 ? d1[k] : static_cast<double>(f1[k]); }
+    __device__ __forceinline__ double get2(int k) const { return k < K64 ? d2[k] : static_cast<double>(f2[k]); }
+    __device__ __forceinline__ void sync_views() {}
+    template <bool TRACK>
+    __device__ __forceinline__ float run(const SosCoef<float, K> &cf, const SosCoefD<K> &cd, float x, double (*hx)[2], double (*hy)[2]) {
+        const double xd = static_cast<double>(x);
+        float acc = 0.f;
+        double vd = xd;
+        float vf = x;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (k < K64) {
+                if (k % KB == 0) vd = xd;
+                const double y = __fma_rn(cd.b0[k], vd, d1[k]);
+                d1[k] = __fma_rn(-cd.a1[k], y, __fma_rn(cd.b1[k], vd, d2[k]));
+                d2[k] = __fma_rn(-cd.a2[k], y, cd.b2[k] * vd);
+                if (TRACK) {
+                    hx[k][1] = hx[k][0];
+                    hx[k][0] = vd;
+                    hy[k][1] = hy[k][0];
+                    hy[k][0] = y;
+                }
+                vd = y;
+                if (k % KB == KB - 1) acc += static_cast<float>(y);
+            } else {
+                if (k % KB == 0) vf = x;
+                const float y = __fmaf_rn(cf.b0[k], vf, f1[k]);
+                f1[k] = __fmaf_rn(cf.na1[k], y, __fmaf_rn(cf.b1[k], vf, f2[k]));
+                f2[k] = __fmaf_rn(cf.na2[k], y, cf.b2[k] * vf);
+                if (TRACK) {
+                    hx[k][1] = hx[k][0];
+                    hx[k][0] = vf;
+                    hy[k][1] = hy[k][0];
+                    hy[k][0] = y;
+                }
+                vf = y;
+                if (k % KB == KB - 1) acc += y;
+            }
+        }
+        return acc;
+    }
+    template <typename IO>
+    __device__ __forceinline__ IO step(const SosCoef<float, K> &cf, const SosCoefD<K> &cd, unsigned, IO x) {
+        return static_cast<IO>(run<false>(cf, cd, static_cast<float>(x), nullptr, nullptr));
+    }
+    template <typename IO>
+    __device__ __forceinline__ IO step_tracked(const SosCoef<float, K> &cf, const SosCoefD<K> &cd, unsigned, IO x, double (&hx)[K][2],
+                                               double (&hy)[K][2]) {
+        return static_cast<IO>(run<true>(cf, cd, static_cast<float>(x), hx, hy));
+    }
+};
+
 template <typename IO, typename CT, int K>
 __global__ void __launch_bounds__(kWarps * 32, CtTraits<CT>::heavy ? (kCtasPerSm + 1) / 2 : kCtasPerSm)
 sos_tile_kernel(const __grid_constant__ SosCoef<typename CtTraits<CT>::Coef, K> cf, const __grid_constant__ SosCoefD<K> cd,
