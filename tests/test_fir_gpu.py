@@ -122,3 +122,18 @@ def test_shapes_and_dtype_like_reference():
         assert y.shape == x.shape and y.dtype == x.dtype and y.is_cuda
     with pytest.raises(ValueError, match="conv_mode"):
         fx.filter.FIR(b, conv_mode="nope")
+
+
+@pytest.mark.parametrize("R", [1, 2, 4])
+@pytest.mark.parametrize("K,T,C", [(3000, 20000, 3), (9000, 50001, 2), (33000, 70000, 5), (65536, 40000, 1)])
+def test_transform_sizes(R, K, T, C, monkeypatch):
+    """The overlap-save path at every transform size (N = 4096 R: a radix-R stage in front of R 4096-point
+    transforms), forced with the TFX_FIR_R developer knob; odd channel counts leave a half-empty pair, T is not
+    a multiple of the hop, K is not a multiple of the partition."""
+    monkeypatch.setenv("TFX_FIR_R", str(R))
+    rng = np.random.default_rng(K + T + R)
+    x = rng.standard_normal((C, T)).astype(np.float32)
+    b = (rng.standard_normal(K) * np.exp(-np.arange(K) / (K / 5.0))).astype(np.float32)
+    want = oracle.fir_causal(x, b)
+    y = fir_causal(torch.from_numpy(x).to(DEV), torch.from_numpy(b), _native.TFX_FIR_OLS)
+    assert rel_to_max(y.cpu().numpy(), want) < TOL

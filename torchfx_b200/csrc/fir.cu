@@ -30,6 +30,7 @@
 //          * Long signals are processed in time slabs so the spectra workspace stays bounded.
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -350,6 +351,156 @@ __global__ void __launch_bounds__(kFftThreads) fir_fwd_kernel(const float *__res
     fft_fwd_tail(v, s, tab, out);
 }
 
+// ------------------------------------------------------------------------------------------
+// Longer transforms, N = 4096 R (R = 2, 4): one radix-R decimation-in-frequency stage in front of
+// R independent 4096-point transforms.  With a[n + 4096 j] the j-th quarter (half) of the block,
+//     U_r = FFT_4096( W_N^{r n} * sum_j a[n + 4096 j] * w_R^{j r} ),  w_R = exp(-2 pi i / R),
+// is the decimated spectrum X[R k + r]; the R sub-spectra are stored one after the other, each in
+// the 4096-point kernel's own output order -- again only ever multiplied point-wise.  Forward: one
+// CTA per (block, pair, r), the R x 16 inputs of a thread are combined in registers (the re-reads of
+// x hit L2).  Inverse: one CTA runs the R sub-transforms in turn and accumulates only the VALID
+// half of the block, a[n + 4096 j] = (1/N) sum_r conj(w_R^{j r} W_N^{r n}) u_r[n] for j >= R/2.
+// Why: the frequency-domain delay line costs P = K / (2048 R) complex MACs per bin and the
+// transforms ~log N per sample (see pick_r for what that measured on B200: not a win in this form).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 mul_mi_pow(float2 v, int e) {  // v * (-i)^e
+    switch (e & 3) {
+        case 1: return make_float2(v.y, -v.x);
+        case 2: return make_float2(-v.x, -v.y);
+        case 3: return make_float2(-v.y, v.x);
+        default: return v;
+    }
+}
+// twn[k] = exp(-2 pi i k / N), k < N
+__global__ void fir_twiddle_n_kernel(float2 *twn, int n_fft) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_fft) {
+        double sn, cs;
+        sincospi(-2.0 * k / n_fft, &sn, &cs);
+        twn[k] = make_float2(static_cast<float>(cs), static_cast<float>(sn));
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(kFftThreads) fir_taps_fft_r_kernel(const float *__restrict__ taps, int64_t K, float2 *__restrict__ H,
+                                                                    const float4 *__restrict__ tab, const float2 *__restrict__ twn) {
+    __shared__ float2 s[kPadN];
+    constexpr int N = kN * R, B = kB * R;
+    const int64_t p = blockIdx.x;
+    const int r = blockIdx.y;
+    float2 v[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const int n = threadIdx.x + 256 * m;
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < R / 2; ++j) {  // the partition fills the first half of the block only
+            const int i = n + kN * j;
+            const int64_t t = p * B + i;
+            const float2 a = make_float2(t < K ? __ldg(&taps[t]) : 0.f, 0.f);
+            const float2 w = mul_mi_pow(a, (4 / R) * j * r);
+            acc.x += w.x;
+            acc.y += w.y;
+        }
+        v[m] = r > 0 ? cmul(acc, __ldg(&twn[r * n])) : acc;
+    }
+    fft_fwd_tail(v, s, tab, H + p * N + r * kN);
+}
+
+template <int R>
+__global__ void __launch_bounds__(kFftThreads) fir_fwd_r_kernel(const float *__restrict__ x, int64_t C, int64_t T, int64_t ldx,
+                                                               int64_t k_first, int64_t nrows, int64_t row0, int64_t ring0,
+                                                               float2 *__restrict__ Z, const float4 *__restrict__ tab,
+                                                               const float2 *__restrict__ twn) {
+    __shared__ float2 s[kPadN];
+    constexpr int N = kN * R, B = kB * R;
+    const int64_t row = row0 + blockIdx.x;
+    const int64_t pair = blockIdx.y;
+    const int r = blockIdx.z;
+    const int64_t k = k_first + row;
+    float2 *out = Z + (pair * nrows + ring_slot(ring0, row, nrows)) * N + r * kN;
+    if (k < 0) {  // block before the start of the signal: all-zero spectrum
+        for (int i = threadIdx.x; i < kN; i += kFftThreads) out[i] = make_float2(0.f, 0.f);
+        return;
+    }
+    const int64_t ca = 2 * pair, cb = 2 * pair + 1;
+    const float *xa = x + ca * ldx;
+    const float *xb = x + (cb < C ? cb : ca) * ldx;
+    const bool has_b = cb < C;
+    const int64_t nbase = (k - 1) * B + threadIdx.x;
+    const bool inside = nbase >= 0 && nbase + N - 1 - threadIdx.x < T;  // block-uniform: the whole block is inside the signal
+    float2 v[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const int n = threadIdx.x + 256 * m;
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const int64_t t = nbase + 256 * m + kN * j;
+            float2 a;
+            if (inside) {
+                a = make_float2(__ldg(&xa[t]), __ldg(&xb[t]));
+            } else {
+                const bool ok = t >= 0 && t < T;
+                a = make_float2(ok ? __ldg(&xa[t]) : 0.f, ok ? __ldg(&xb[t]) : 0.f);
+            }
+            if (!has_b) a.y = 0.f;
+            const float2 w = mul_mi_pow(a, (4 / R) * j * r);
+            acc.x += w.x;
+            acc.y += w.y;
+        }
+        v[m] = r > 0 ? cmul(acc, __ldg(&twn[r * n])) : acc;
+    }
+    fft_fwd_tail(v, s, tab, out);
+}
+
+template <int R>
+__global__ void __launch_bounds__(kFftThreads, R == 2 ? 2 : 1) fir_inv_r_kernel(const float2 *__restrict__ Y, float *__restrict__ y, int64_t C, int64_t T,
+                                                               int64_t ldy, int64_t k_first, int64_t nout,
+                                                               const float4 *__restrict__ tab, const float2 *__restrict__ twn) {
+    __shared__ float2 s[kPadN];
+    constexpr int N = kN * R, B = kB * R, HV = R / 2;  // HV valid quarters (halves) of kN samples each
+    const int64_t jb = blockIdx.x;
+    const int64_t pair = blockIdx.y;
+    float2 acc[HV][16];
+#pragma unroll
+    for (int h = 0; h < HV; ++h)
+#pragma unroll
+        for (int m = 0; m < 16; ++m) acc[h][m] = make_float2(0.f, 0.f);
+    float2 v[16];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (r > 0) __syncthreads();  // everyone is done reading the previous sub-transform's tile
+        fft_inv(v, s, tab, Y + (pair * nout + jb) * N + r * kN);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int n = threadIdx.x + 256 * m;
+            const float2 t = r > 0 ? cmulc(v[m], __ldg(&twn[r * n])) : v[m];
+#pragma unroll
+            for (int h = 0; h < HV; ++h) {
+                const float2 w = mul_mi_pow(t, -(4 / R) * (h + HV) * r);  // conj(w_R^{j r}) = (-i)^{-(4/R) j r}
+                acc[h][m].x += w.x;
+                acc[h][m].y += w.y;
+            }
+        }
+    }
+    const int64_t ca = 2 * pair, cb = 2 * pair + 1;
+    const float scale = 1.0f / N;
+    float *ya = y + ca * ldy;
+    float *yb = y + cb * ldy;
+    const bool has_b = cb < C;
+#pragma unroll
+    for (int h = 0; h < HV; ++h)
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int64_t n = (k_first + jb) * B + h * kN + threadIdx.x + 256 * m;
+            if (n < T) {
+                ya[n] = acc[h][m].x * scale;
+                if (has_b) yb[n] = acc[h][m].y * scale;
+            }
+        }
+}
+
 // 16-byte cp.async that writes zeros instead when !valid (src-size 0: nothing is read).
 __device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gmem_src, bool valid) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
@@ -372,7 +523,7 @@ struct MacItem {
 };
 __global__ void __launch_bounds__(512, 1) fir_mac_kernel(const float2 *__restrict__ Z, const float2 *__restrict__ H,
                                                         float2 *__restrict__ Y, int P, int nrows, int ring0, int nvalid,
-                                                        int nout, int ntiles_j, int ntiles) {
+                                                        int nout, int ntiles_j, int ntiles, int n_fft) {
     extern __shared__ float2 smc[];
     constexpr int kBufElems = (kMacRows + kMacPc) * kMacBins;  // Zs [159][64] then Hs [32][64]
     constexpr int R = kMacPerThread;
@@ -383,8 +534,8 @@ __global__ void __launch_bounds__(512, 1) fir_mac_kernel(const float2 *__restric
     auto decode = [&](int t, int pc) {
         MacItem it;
         it.pc = pc;
-        it.f0 = (t % (kN / kMacBins)) * kMacBins;
-        t /= (kN / kMacBins);
+        it.f0 = (t % (n_fft / kMacBins)) * kMacBins;
+        t /= (n_fft / kMacBins);
         it.j0 = (t % ntiles_j) * kMacBlocks;
         it.pair = t / ntiles_j;
         return it;
@@ -393,7 +544,7 @@ __global__ void __launch_bounds__(512, 1) fir_mac_kernel(const float2 *__restric
     auto chunk_parts = [&](int pc) { return min(kMacPc, ((P - pc * kMacPc) + 7) & ~7); };
     auto issue = [&](const MacItem &it, float2 *buf) {
         const int npl = chunk_parts(it.pc);
-        const float2 *Zp = Z + static_cast<int64_t>(it.pair) * nrows * kN + it.f0;
+        const float2 *Zp = Z + static_cast<int64_t>(it.pair) * nrows * n_fft + it.f0;
         // rows needed: j + (P-1) - p for j in [j0, j0 + kMacBlocks), p in [32pc, 32pc+npl)
         const int row_lo = it.j0 + (P - 1) - (it.pc * kMacPc + kMacPc - 1);
         const int r_first = kMacPc - npl;  // local rows below this belong to partitions that are not run
@@ -403,14 +554,14 @@ __global__ void __launch_bounds__(512, 1) fir_mac_kernel(const float2 *__restric
             const bool ok = row >= 0 && row < nvalid;
             int slot = ring0 + row;
             slot = slot >= nrows ? slot - nrows : slot;
-            cp_async16_zfill(buf + r * kMacBins + 2 * q, Zp + (ok ? slot * kN : 0) + 2 * q, ok);
+            cp_async16_zfill(buf + r * kMacBins + 2 * q, Zp + (ok ? static_cast<int64_t>(slot) * n_fft : 0) + 2 * q, ok);
         }
         float2 *hb = buf + kMacRows * kMacBins;
         for (int i = threadIdx.x; i < npl * 32; i += 512) {
             const int pl = i >> 5, q = i & 31;
             const int p = it.pc * kMacPc + pl;
             const bool ok = p < P;
-            cp_async16_zfill(hb + pl * kMacBins + 2 * q, H + (ok ? p * kN : 0) + it.f0 + 2 * q, ok);
+            cp_async16_zfill(hb + pl * kMacBins + 2 * q, H + (ok ? static_cast<int64_t>(p) * n_fft : 0) + it.f0 + 2 * q, ok);
         }
         cp_async_commit();
     };
@@ -495,11 +646,11 @@ __global__ void __launch_bounds__(512, 1) fir_mac_kernel(const float2 *__restric
             }
         }
         if (cur.pc == nchunks - 1) {
-            float2 *Yp = Y + static_cast<int64_t>(cur.pair) * nout * kN + cur.f0 + fl;
+            float2 *Yp = Y + static_cast<int64_t>(cur.pair) * nout * n_fft + cur.f0 + fl;
 #pragma unroll
             for (int jj = 0; jj < R; ++jj) {
                 const int j = cur.j0 + kg * R + jj;
-                if (j < nout) Yp[static_cast<int64_t>(j) * kN] = acc[jj];
+                if (j < nout) Yp[static_cast<int64_t>(j) * n_fft] = acc[jj];
             }
         }
         __syncthreads();  // buffer b is free for the fetch issued in the next iteration
@@ -537,18 +688,38 @@ __global__ void __launch_bounds__(kFftThreads) fir_inv_kernel(const float2 *__re
 }
 
 struct OlsLayout {
+    int R;  // transform size N = 4096 R, partition / hop B = 2048 R
+    int64_t N, B;
     int64_t P, npairs, nblk, slab, nrows;  // slab = output blocks per slab, nrows = slab + P - 1
-    size_t off_tw, off_H, off_Z, off_Y, total;
+    size_t off_tw, off_twn, off_H, off_Z, off_Y, total;
 };
+
+// Transform size.  The delay line costs P = K / (2048 R) complex MACs per bin, so a longer transform
+// halves / quarters the MAC work -- but measured on B200 for the 65 536-tap config (profiles/r1_fir.md)
+// R = 2 and R = 4 LOSE (8.8 -> 10.2 -> 14.0 ms): every sub-transform CTA re-reads all R parts of the block
+// (forward kernel 2.2x / 4x slower), the register-heavy inverse runs at 1-2 CTAs per SM, and the MAC, now
+// with half the flops, drops onto its own HBM bound.  R = 1 therefore stays the default for every K;
+// TFX_FIR_R = 2 | 4 keeps the longer transforms reachable (parity-tested) for further work.
+int pick_r(int64_t K) {
+    (void)K;
+    if (const char *e = std::getenv("TFX_FIR_R")) {
+        const int r = std::atoi(e);
+        if (r == 1 || r == 2 || r == 4) return r;
+    }
+    return 1;
+}
 
 OlsLayout ols_layout(int64_t C, int64_t T, int64_t K) {
     OlsLayout L{};
-    L.P = (K + kB - 1) / kB;
+    L.R = pick_r(K);
+    L.N = static_cast<int64_t>(kN) * L.R;
+    L.B = static_cast<int64_t>(kB) * L.R;
+    L.P = (K + L.B - 1) / L.B;
     L.npairs = (C + 1) / 2;
-    L.nblk = (T + kB - 1) / kB;
-    // Slab: as many blocks as keep Z + Y near 1 GiB, at least 4P so the P-1 recomputed
-    // history blocks stay a small fraction.
-    const int64_t per_block = L.npairs * static_cast<int64_t>(kN) * static_cast<int64_t>(sizeof(float2)) * 2;
+    L.nblk = (T + L.B - 1) / L.B;
+    // Slab: as many blocks as keep Z + Y near 1 GiB, at least 4P so the ring's P-1 history rows
+    // stay a small fraction, and at least one MAC tile.
+    const int64_t per_block = L.npairs * L.N * static_cast<int64_t>(sizeof(float2)) * 2;
     int64_t slab = (int64_t(1) << 30) / std::max<int64_t>(per_block, 1);
     slab = std::max<int64_t>(slab, 4 * L.P);
     slab = std::max<int64_t>(slab, kMacBlocks);
@@ -558,10 +729,11 @@ OlsLayout ols_layout(int64_t C, int64_t T, int64_t K) {
     L.nrows = slab + L.P - 1;
     auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
     L.off_tw = 0;
-    L.off_H = align(kTwBytes);
-    L.off_Z = align(L.off_H + static_cast<size_t>(L.P) * kN * sizeof(float2));
-    L.off_Y = align(L.off_Z + static_cast<size_t>(L.npairs) * L.nrows * kN * sizeof(float2));
-    L.total = align(L.off_Y + static_cast<size_t>(L.npairs) * L.slab * kN * sizeof(float2));
+    L.off_twn = align(kTwBytes);
+    L.off_H = align(L.off_twn + static_cast<size_t>(L.N) * sizeof(float2));
+    L.off_Z = align(L.off_H + static_cast<size_t>(L.P) * L.N * sizeof(float2));
+    L.off_Y = align(L.off_Z + static_cast<size_t>(L.npairs) * L.nrows * L.N * sizeof(float2));
+    L.total = align(L.off_Y + static_cast<size_t>(L.npairs) * L.slab * L.N * sizeof(float2));
     return L;
 }
 
@@ -615,12 +787,23 @@ int tfx_fir_f32(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     float2 *tw2 = reinterpret_cast<float2 *>(ws + L.off_tw);
     const float4 *tw = reinterpret_cast<const float4 *>(tw2);
+    float2 *twn = reinterpret_cast<float2 *>(ws + L.off_twn);
     float2 *H = reinterpret_cast<float2 *>(ws + L.off_H);
     float2 *Z = reinterpret_cast<float2 *>(ws + L.off_Z);
     float2 *Y = reinterpret_cast<float2 *>(ws + L.off_Y);
+    const unsigned P = static_cast<unsigned>(L.P), npairs = static_cast<unsigned>(L.npairs);
     fir_twiddle_kernel<<<(kTwEntries + 255) / 256, 256, 0, stream>>>(tw2);
     TFX_CHECK_LAUNCH("fir_twiddle_kernel");
-    fir_taps_fft_kernel<<<static_cast<unsigned>(L.P), kFftThreads, 0, stream>>>(taps, K, H, tw);
+    if (L.R > 1) {
+        fir_twiddle_n_kernel<<<static_cast<unsigned>((L.N + 255) / 256), 256, 0, stream>>>(twn, static_cast<int>(L.N));
+        TFX_CHECK_LAUNCH("fir_twiddle_n_kernel");
+    }
+    if (L.R == 1)
+        fir_taps_fft_kernel<<<P, kFftThreads, 0, stream>>>(taps, K, H, tw);
+    else if (L.R == 2)
+        fir_taps_fft_r_kernel<2><<<dim3(P, 2), kFftThreads, 0, stream>>>(taps, K, H, tw, twn);
+    else
+        fir_taps_fft_r_kernel<4><<<dim3(P, 4), kFftThreads, 0, stream>>>(taps, K, H, tw, twn);
     TFX_CHECK_LAUNCH("fir_taps_fft_kernel");
     const size_t mac_smem = 2 * sizeof(float2) * (kMacRows + kMacPc) * kMacBins;  // double buffer
     TFX_ENSURE_SMEM(fir_mac_kernel, static_cast<int>(mac_smem));
@@ -632,20 +815,30 @@ int tfx_fir_f32(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int
         // ring: only the new blocks are transformed.  The first slab's history (k < 0) is written as zeros.
         const int64_t row0 = k0 > 0 ? L.P - 1 : 0;
         const int64_t ring0 = k0 % nrows;
-        fir_fwd_kernel<<<dim3(static_cast<unsigned>(nout + L.P - 1 - row0), static_cast<unsigned>(L.npairs)), kFftThreads, 0,
-                         stream>>>(x, C, T, ldx, k_first, nrows, row0, ring0, Z, tw);
+        const unsigned nfwd = static_cast<unsigned>(nout + L.P - 1 - row0);
+        if (L.R == 1)
+            fir_fwd_kernel<<<dim3(nfwd, npairs), kFftThreads, 0, stream>>>(x, C, T, ldx, k_first, nrows, row0, ring0, Z, tw);
+        else if (L.R == 2)
+            fir_fwd_r_kernel<2><<<dim3(nfwd, npairs, 2), kFftThreads, 0, stream>>>(x, C, T, ldx, k_first, nrows, row0, ring0, Z, tw, twn);
+        else
+            fir_fwd_r_kernel<4><<<dim3(nfwd, npairs, 4), kFftThreads, 0, stream>>>(x, C, T, ldx, k_first, nrows, row0, ring0, Z, tw, twn);
         TFX_CHECK_LAUNCH("fir_fwd_kernel");
         const int64_t ntiles_j = (nout + kMacBlocks - 1) / kMacBlocks;
-        const int64_t ntiles = L.npairs * ntiles_j * (kN / kMacBins);
+        const int64_t ntiles = L.npairs * ntiles_j * (L.N / kMacBins);
         TFX_REQUIRE(ntiles < (int64_t(1) << 31) && nrows < (int64_t(1) << 19), "fir: slab too large for the MAC kernel's 32-bit indexing");
         const unsigned mac_grid = static_cast<unsigned>(std::min<int64_t>(ntiles, sm_count()));
         fir_mac_kernel<<<mac_grid, 512, mac_smem, stream>>>(Z, H, Y, static_cast<int>(L.P), static_cast<int>(nrows),
                                                           static_cast<int>(ring0), static_cast<int>(nout + L.P - 1),
                                                           static_cast<int>(nout), static_cast<int>(ntiles_j),
-                                                          static_cast<int>(ntiles));
+                                                          static_cast<int>(ntiles), static_cast<int>(L.N));
         TFX_CHECK_LAUNCH("fir_mac_kernel");
-        fir_inv_kernel<<<dim3(static_cast<unsigned>(nout), static_cast<unsigned>(L.npairs)), kFftThreads, 0, stream>>>(
-            Y, y, C, T, ldy, k0, nout, tw);
+        const unsigned ninv = static_cast<unsigned>(nout);
+        if (L.R == 1)
+            fir_inv_kernel<<<dim3(ninv, npairs), kFftThreads, 0, stream>>>(Y, y, C, T, ldy, k0, nout, tw);
+        else if (L.R == 2)
+            fir_inv_r_kernel<2><<<dim3(ninv, npairs), kFftThreads, 0, stream>>>(Y, y, C, T, ldy, k0, nout, tw, twn);
+        else
+            fir_inv_r_kernel<4><<<dim3(ninv, npairs), kFftThreads, 0, stream>>>(Y, y, C, T, ldy, k0, nout, tw, twn);
         TFX_CHECK_LAUNCH("fir_inv_kernel");
     }
     return TFX_OK;
