@@ -33,6 +33,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace tfx {
 namespace {
@@ -47,6 +48,12 @@ constexpr int kMacBlocks = 128;       // output blocks per MAC tile
 constexpr int kMacPerThread = 16;     // consecutive blocks per thread (512 threads = 64 bins x 8 groups)
 constexpr int kMacPc = 32;            // partitions per shared-memory chunk
 constexpr int kMacRows = kMacBlocks + kMacPc - 1;  // 159 spectra rows staged per chunk
+// 1: stage the MAC tiles with cp.async.bulk + mbarriers instead of LDGSTS.  Measured SLOWER on B200 (config 3:
+// 12.08 ms against 8.55 ms; profiles/r1_fir.md) -- 191 512-byte bulk copies per item run into the per-SM bulk-copy
+// request rate -- so it is off; kept as a build variant (tools/build_stack_variants.sh, UNIT=fir).
+#ifndef TFX_MAC_BULK
+#define TFX_MAC_BULK 0
+#endif
 
 // ------------------------------------------------------------------------------------------
 // DIRECT
@@ -501,12 +508,14 @@ __global__ void __launch_bounds__(kFftThreads, R == 2 ? 2 : 1) fir_inv_r_kernel(
         }
 }
 
+#if !TFX_MAC_BULK
 // 16-byte cp.async that writes zeros instead when !valid (src-size 0: nothing is read).
 __device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gmem_src, bool valid) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
                  "r"(valid ? 16 : 0)
                  : "memory");
 }
+#endif
 
 // Y[pair][j] = sum_p H[p] . Z[pair][j + (P-1) - p],  j in [0, nout)
 //
@@ -542,6 +551,55 @@ __global__ void __launch_bounds__(512, 1) fir_mac_kernel(const float2 *__restric
     };
     // partitions of chunk pc that exist, rounded up to the unroll step of the short path
     auto chunk_parts = [&](int pc) { return min(kMacPc, ((P - pc * kMacPc) + 7) & ~7); };
+#if TFX_MAC_BULK
+    // Staging by the bulk-copy engine: one 512-byte `cp.async.bulk` per spectra / taps row, issued by the lanes
+    // of warp 0 and counted on the buffer's mbarrier -- ~12 instructions per item instead of ~300 per thread
+    // (the LDGSTS version spent a quarter of its issue slots on staging addresses).  Rows outside the signal
+    // or beyond the last partition are zero-filled with ordinary stores.
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smc + 2 * kBufElems);
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_proxy_async_smem();
+    }
+    __syncthreads();
+    auto issue = [&](const MacItem &it, float2 *buf, uint64_t *bar) {
+        if (threadIdx.x >= 32) return;
+        const int lane = threadIdx.x;
+        const int npl = chunk_parts(it.pc);
+        const float2 *Zp = Z + static_cast<int64_t>(it.pair) * nrows * n_fft + it.f0;
+        const int row_lo = it.j0 + (P - 1) - (it.pc * kMacPc + kMacPc - 1);
+        const int r_first = kMacPc - npl;  // local rows below this belong to partitions that are not run
+        const int n_ok = max(min(row_lo + kMacRows, nvalid) - max(row_lo + r_first, 0), 0);
+        const int h_ok = max(min(npl, P - it.pc * kMacPc), 0);
+        if (lane == 0) mbar_arrive_expect_tx(bar, 512u * static_cast<uint32_t>(n_ok + h_ok));
+        fence_proxy_async_smem();
+        __syncwarp();
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = r_first + lane; r < kMacRows; r += 32) {
+            const int row = row_lo + r;
+            float2 *dst = buf + r * kMacBins;
+            if (row >= 0 && row < nvalid) {
+                int slot = ring0 + row;
+                slot = slot >= nrows ? slot - nrows : slot;
+                bulk_load_1d(dst, Zp + static_cast<int64_t>(slot) * n_fft, 512u, bar);
+            } else {
+                for (int q = 0; q < 32; ++q) reinterpret_cast<float4 *>(dst)[q] = zero;
+            }
+        }
+        float2 *hb = buf + kMacRows * kMacBins;
+        for (int pl = lane; pl < npl; pl += 32) {
+            const int p = it.pc * kMacPc + pl;
+            float2 *dst = hb + pl * kMacBins;
+            if (p < P) {
+                bulk_load_1d(dst, H + static_cast<int64_t>(p) * n_fft + it.f0, 512u, bar);
+            } else {
+                for (int q = 0; q < 32; ++q) reinterpret_cast<float4 *>(dst)[q] = zero;
+            }
+        }
+    };
+    unsigned phase = 0;  // bit b: parity to wait for on buffer b
+#else
     auto issue = [&](const MacItem &it, float2 *buf) {
         const int npl = chunk_parts(it.pc);
         const float2 *Zp = Z + static_cast<int64_t>(it.pair) * nrows * n_fft + it.f0;
@@ -566,6 +624,7 @@ __global__ void __launch_bounds__(512, 1) fir_mac_kernel(const float2 *__restric
         cp_async_commit();
     };
 
+#endif
     float2 acc[R];
     // this CTA's work: tiles blockIdx.x, blockIdx.x + gridDim.x, ...; within a tile chunks 0..nchunks-1
     int tile = blockIdx.x;
@@ -573,7 +632,12 @@ __global__ void __launch_bounds__(512, 1) fir_mac_kernel(const float2 *__restric
     if (tile >= ntiles) return;
     MacItem cur = decode(tile, pc);
     int b = 0;
+#if TFX_MAC_BULK
+    issue(cur, smc, &bars[0]);
+    __syncthreads();  // zero-filled rows of the first item are visible to everyone
+#else
     issue(cur, smc);
+#endif
     while (tile < ntiles) {
         int ntile = tile;
         int npc = pc + 1;
@@ -582,6 +646,14 @@ __global__ void __launch_bounds__(512, 1) fir_mac_kernel(const float2 *__restric
             ntile = tile + gridDim.x;
         }
         MacItem nxt = cur;
+#if TFX_MAC_BULK
+        if (ntile < ntiles) {
+            nxt = decode(ntile, npc);
+            issue(nxt, smc + (b ^ 1) * kBufElems, &bars[b ^ 1]);
+        }
+        mbar_wait(&bars[b], (phase >> b) & 1u);
+        phase ^= 1u << b;
+#else
         if (ntile < ntiles) {
             nxt = decode(ntile, npc);
             issue(nxt, smc + (b ^ 1) * kBufElems);
@@ -590,6 +662,7 @@ __global__ void __launch_bounds__(512, 1) fir_mac_kernel(const float2 *__restric
             cp_async_wait<0>();
         }
         __syncthreads();
+#endif
         if (cur.pc == 0) {
 #pragma unroll
             for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
@@ -653,7 +726,7 @@ __global__ void __launch_bounds__(512, 1) fir_mac_kernel(const float2 *__restric
                 if (j < nout) Yp[static_cast<int64_t>(j) * n_fft] = acc[jj];
             }
         }
-        __syncthreads();  // buffer b is free for the fetch issued in the next iteration
+        __syncthreads();  // buffer b is free for the fetch issued in the next iteration (and the other buffer's zero rows are visible)
         cur = nxt;
         tile = ntile;
         pc = npc;
@@ -805,7 +878,7 @@ int tfx_fir_f32(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int
     else
         fir_taps_fft_r_kernel<4><<<dim3(P, 4), kFftThreads, 0, stream>>>(taps, K, H, tw, twn);
     TFX_CHECK_LAUNCH("fir_taps_fft_kernel");
-    const size_t mac_smem = 2 * sizeof(float2) * (kMacRows + kMacPc) * kMacBins;  // double buffer
+    const size_t mac_smem = 2 * sizeof(float2) * (kMacRows + kMacPc) * kMacBins + 16;  // double buffer + two mbarriers
     TFX_ENSURE_SMEM(fir_mac_kernel, static_cast<int>(mac_smem));
     for (int64_t k0 = 0; k0 < L.nblk; k0 += L.slab) {
         const int64_t nout = std::min<int64_t>(L.slab, L.nblk - k0);
