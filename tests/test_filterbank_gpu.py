@@ -315,3 +315,66 @@ def test_sum_tile_mixed_precision_prefix(n, kb, n_low):
     finally:
         _ops.set_default_precision("auto")
     assert rel_to_max(y, y64) < 2e-6
+
+
+# ---- SUM banks of 9..32 bands on bank_stack_kernel (per-warp partial tiles, reduced in warp order) ---------
+
+@pytest.mark.parametrize("n,kb", [(9, 1), (12, 1), (17, 1), (32, 1), (5, 2), (11, 2), (6, 3)])
+@pytest.mark.parametrize("C", [32, 61])
+def test_sum_many_bands_vs_oracle(n, kb, C):
+    from torchfx_b200.filter._sosbank import SosBank
+
+    rng = np.random.default_rng(7000 + 10 * n + kb + C)
+    T = 60001
+    x = (0.1 * rng.standard_normal((C, T))).astype(np.float32)
+
+    def mk():
+        if kb == 1:
+            return [fx.filter.BiquadBPF(40.0 * (1.2 ** i), 1.414, 48000) for i in range(n)]  # the low ones need float64
+        if kb == 2:
+            return [fx.filter.LoButterworth(500.0 * (1.3 ** i), order=4, fs=48000) for i in range(n)]
+        return [fx.filter.HiButterworth(100.0 * (1.5 ** i), order=6, fs=48000) for i in range(n)]
+
+    filters = mk()
+    bank = SosBank(filters, mode="sum")
+    xt = torch.from_numpy(x).to(DEV)
+    before = _native.kernel_launches()
+    y = torch.cat([bank(xt[:, :1]), bank(xt[:, 1:25001]), bank(xt[:, 25001:])], dim=1).cpu().numpy()
+    assert _native.kernel_launches() - before <= 6  # three calls of (warm-up +) main, not 3 n launches
+    sos = np.stack([f._sos.numpy() for f in filters])
+    want = oracle.filterbank_sum(x, sos)
+    assert y.shape == want.shape
+    assert rel_to_max(y, want) < TOL
+    other = SosBank(mk(), mode="sum")
+    other.flags = _native.TFX_NO_TILE  # band-per-lane kernel: same sum in strict band order
+    y2 = other(xt).cpu().numpy()
+    assert rel_to_max(y2, y) < 5e-6
+    for i in {0, n // 2, n - 1}:
+        _, wsx, wsy = oracle.sos_cascade(x, sos[i])
+        np.testing.assert_allclose(filters[i]._state_x.cpu().numpy(), wsx, rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(filters[i]._state_y.cpu().numpy(), wsy, rtol=1e-3, atol=1e-5 * np.abs(wsy).max())
+
+
+def test_sum_8192_lanes_linearity():
+    """BASELINE configs[4] read literally: 32 biquads added (`+`) over 256 channels = 8192 biquad lanes, 20 s.
+    Linearity of the bank and oracle parity on 3 channels; one warm-up + one main launch."""
+    from torchfx_b200.filter._sosbank import SosBank
+
+    C, T = 256, 960000
+    g = torch.Generator(device=DEV).manual_seed(21)
+    x1 = 0.1 * torch.randn(C, T, device=DEV, generator=g)
+    x2 = 0.1 * torch.randn(C, T, device=DEV, generator=g)
+    mk = lambda: [fx.filter.BiquadBPF(20.0 * (1000.0 ** (i / 31.0)), 1.414, 48000) for i in range(32)]
+    before = _native.kernel_launches()
+    y1 = SosBank(mk(), mode="sum")(x1)
+    assert _native.kernel_launches() - before == 2
+    y2 = SosBank(mk(), mode="sum")(x2)
+    y12 = SosBank(mk(), mode="sum")(0.5 * x1 + x2)
+    err = (y12 - (0.5 * y1 + y2)).abs().max().item() / y12.abs().max().item()
+    assert err < 5e-6
+    sel = [0, 77, 255]
+    filters = mk()
+    for f in filters:
+        f.compute_coefficients()
+    want = oracle.filterbank_sum(x1[sel].cpu().numpy(), np.stack([f._sos.numpy() for f in filters]))
+    assert rel_to_max(y1[sel].cpu().numpy(), want) < TOL

@@ -169,6 +169,20 @@ def cfg5():
         out["sum" if prec == "auto" else f"sum_{prec}"] = {
             "ms": round(ms, 3), "Gsamples_s": round(C * T / ms / 1e6, 1), "G_lane_samples_s": round(8 * C * T / ms / 1e6, 1),
             "GBps": round(8 * C * T / ms / 1e6, 1), "frac_hbm": round(8 * C * T / ms / 1e6 / PEAK, 3), "launches": nl}
+    # BASELINE configs[4] read literally: 32 biquads added over 256 channels (8192 biquad lanes)
+    x32 = x[:256]
+    fl32 = [fx.filter.BiquadBPF(20.0 * (1000.0 ** (i / 31.0)), 1.414, FS) for i in range(32)]
+    comb32 = fx.filter._base.ParallelFilterCombination(*fl32)
+    def run_sum32():
+        for f in fl32:
+            f.reset_state()
+        return comb32(x32)
+    for prec in ("f32", "auto"):
+        _ops.set_default_precision(prec)
+        ms, nl = timed(run_sum32, reps=3)
+        out["sum32" if prec == "auto" else f"sum32_{prec}"] = {
+            "ms": round(ms, 3), "Gsamples_s": round(256 * T / ms / 1e6, 1), "G_lane_samples_s": round(32 * 256 * T / ms / 1e6, 1),
+            "GBps": round(8 * 256 * T / ms / 1e6, 1), "launches": nl}
     for f in fl:
         f.reset_state()
     y = comb(x[:2, : 1 << 17])

@@ -68,6 +68,7 @@ struct StackGeom {
     int bpw;            // band slots per warp = ceil(n_bands / W)
     uint32_t f64_mask;  // bit b: band b runs the float64 recurrence
     int vec_ok;
+    int sum;          // 1: SUM mode -- the bands are added (warp partials in slot order, then warps in order) into y[C, T]
     int band_id[32];  // global band index of local band b (y plane and state block)
     int warm_b[32];   // warm-up samples band b needs (multiple of 64, <= warm)
 };
@@ -88,7 +89,27 @@ __device__ __forceinline__ void store_row16(float *gptr, const float4 &v) {
 __device__ __forceinline__ int elem_offset(int r, int e) { return col_offset(r, e >> 2) + (e & 3) * 4; }
 
 // One band over one chunk of my row: state in and out of shared memory.
-template <typename CT, int KB, bool WRITE>
+// OUT: 0 = no output (warm-up), 1 = write the band's tile, 2 = add onto the tile (SUM mode, later bands of a warp)
+__device__ __forceinline__ void emit4(unsigned char *p, const float4 &a, int out_mode) {
+    if (out_mode == 1) {
+        *reinterpret_cast<float4 *>(p) = a;
+    } else if (out_mode == 2) {
+        float4 o = *reinterpret_cast<const float4 *>(p);
+        o.x += a.x;
+        o.y += a.y;
+        o.z += a.z;
+        o.w += a.w;
+        *reinterpret_cast<float4 *>(p) = o;
+    }
+}
+__device__ __forceinline__ void emit1(unsigned char *p, float y, int out_mode) {
+    if (out_mode == 1)
+        *reinterpret_cast<float *>(p) = y;
+    else if (out_mode == 2)
+        *reinterpret_cast<float *>(p) += y;
+}
+
+template <typename CT, int KB, int OUT>
 __device__ __forceinline__ void band_chunk(const StackCoef<KB> &cd, int b, const unsigned char *xin, unsigned char *out, double2 *st,
                                            int lane, int cnt) {
     CT b0[KB], b1[KB], b2[KB], na1[KB], na2[KB], s1[KB], s2[KB];
@@ -124,13 +145,13 @@ __device__ __forceinline__ void band_chunk(const StackCoef<KB> &cd, int b, const
             a.y = step(a.y);
             a.z = step(a.z);
             a.w = step(a.w);
-            if (WRITE) *reinterpret_cast<float4 *>(out + col_offset(lane, v)) = a;
+            emit4(out + col_offset(lane, v), a, OUT);
             a = nxt;
         }
     } else {
         for (int e = 0; e < cnt; ++e) {
             const float y = step(*reinterpret_cast<const float *>(xin + elem_offset(lane, e)));
-            if (WRITE) *reinterpret_cast<float *>(out + elem_offset(lane, e)) = y;
+            emit1(out + elem_offset(lane, e), y, OUT);
         }
     }
 #pragma unroll
@@ -140,7 +161,7 @@ __device__ __forceinline__ void band_chunk(const StackCoef<KB> &cd, int b, const
 // Float64 band: reads the CTA's float64 copy of the input tile (converted ONCE per tile, not once
 // per band -- F2F runs at 16 lanes/clk/SM, so a per-band conversion costs the FP64 pipe more than
 // the band's five DFMAs), rounds only the output.
-template <int KB, bool WRITE>
+template <int KB, int OUT>
 __device__ __forceinline__ void band_chunk64(const StackCoef<KB> &cd, int b, const unsigned char *x64, unsigned char *out, double2 *st,
                                              int lane, int cnt) {
     double b0[KB], b1[KB], b2[KB], na1[KB], na2[KB], s1[KB], s2[KB];
@@ -176,13 +197,13 @@ __device__ __forceinline__ void band_chunk64(const StackCoef<KB> &cd, int b, con
             o.y = step(a.y);
             o.z = step(c.x);
             o.w = step(c.y);
-            if (WRITE) *reinterpret_cast<float4 *>(out + col_offset(lane, v)) = o;
+            emit4(out + col_offset(lane, v), o, OUT);
             a = nxt;
         }
     } else {
         for (int e = 0; e < cnt; ++e) {
             const float y = step(*reinterpret_cast<const double *>(x64 + col_offset(lane, e >> 1) + (e & 1) * 8));
-            if (WRITE) *reinterpret_cast<float *>(out + elem_offset(lane, e)) = y;
+            emit1(out + elem_offset(lane, e), y, OUT);
         }
     }
 #pragma unroll
@@ -193,7 +214,7 @@ __device__ __forceinline__ void band_chunk64(const StackCoef<KB> &cd, int b, con
 // recording every section's input / output: that IS the DF1 state handed back.
 template <typename CT, int KB>
 __device__ __forceinline__ void band_tail(const StackCoef<KB> &cd, const StackGeom &g, int b, int64_t gb, int64_t c, int64_t n1, int tail,
-                                          bool from_true_state, const double2 *st, int lane) {
+                                          bool from_true_state, const double2 *st, int lane, float *partial, bool first) {
     CT s1[KB], s2[KB], hx[KB][2], hy[KB][2];
 #pragma unroll
     for (int k = 0; k < KB; ++k) {
@@ -225,7 +246,12 @@ __device__ __forceinline__ void band_tail(const StackCoef<KB> &cd, const StackGe
             hy[k][0] = y;
             v = y;
         }
-        g.y[gb * g.ldb + c * g.ldy + n] = static_cast<float>(v);
+        if (partial == nullptr)
+            g.y[gb * g.ldb + c * g.ldy + n] = static_cast<float>(v);
+        else if (first)  // SUM mode: this warp's partial sum of the tail samples, [e][lane]
+            partial[e * 32 + lane] = static_cast<float>(v);
+        else
+            partial[e * 32 + lane] += static_cast<float>(v);
     }
 #pragma unroll
     for (int k = 0; k < KB; ++k) {
@@ -361,17 +387,33 @@ bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constan
                 if (n0 + base < start_b) continue;  // this band's window has not begun yet
                 if (live) {
                     if (is64)
-                        band_chunk64<KB, false>(cd, b, x64, nullptr, st, lane, cnt);
+                        band_chunk64<KB, 0>(cd, b, x64, nullptr, st, lane, cnt);
                     else
-                        band_chunk<float, KB, false>(cd, b, tile, nullptr, st, lane, cnt);
+                        band_chunk<float, KB, 0>(cd, b, tile, nullptr, st, lane, cnt);
+                }
+                continue;
+            }
+            if (g.sum) {  // accumulate this warp's bands in its tile; reduced over the warps below
+                if (live) {
+                    if (slot == 0) {
+                        if (is64)
+                            band_chunk64<KB, 1>(cd, b, x64, otile, st, lane, cnt);
+                        else
+                            band_chunk<float, KB, 1>(cd, b, tile, otile, st, lane, cnt);
+                    } else {
+                        if (is64)
+                            band_chunk64<KB, 2>(cd, b, x64, otile, st, lane, cnt);
+                        else
+                            band_chunk<float, KB, 2>(cd, b, tile, otile, st, lane, cnt);
+                    }
                 }
                 continue;
             }
             if (live) {
                 if (is64)
-                    band_chunk64<KB, true>(cd, b, x64, otile, st, lane, cnt);
+                    band_chunk64<KB, 1>(cd, b, x64, otile, st, lane, cnt);
                 else
-                    band_chunk<float, KB, true>(cd, b, tile, otile, st, lane, cnt);
+                    band_chunk<float, KB, 1>(cd, b, tile, otile, st, lane, cnt);
             }
             __syncwarp();
             // ---- the band's [32 x 64] tile leaves as coalesced rows of y[gb] ---------------------
@@ -398,6 +440,38 @@ bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constan
             }
             __syncwarp();
         }
+        if (g.sum && !warm_pass) {
+            // ---- SUM: add the warps' partial tiles in warp order; the CTA stores ONE tile of y ----------
+            __syncthreads();
+            const unsigned char *t0 = base_sm + (kStagesX + 2) * kTileBytes;
+            const int wb = warp_bytes(g.bpw, KB);
+            float *yt = g.y + n0 + base;
+            if (cnt == kCH && g.vec_ok) {
+                for (int idx = tid; idx < 32 * kNV; idx += nthreads) {
+                    const int r = idx / kNV, p = idx % kNV;
+                    if (r >= nrows) continue;
+                    const int off = col_offset(r, p);
+                    float4 acc = *reinterpret_cast<const float4 *>(t0 + off);
+                    for (int w = 1; w < g.W; ++w) {
+                        const float4 a = *reinterpret_cast<const float4 *>(t0 + w * wb + off);
+                        acc.x += a.x;
+                        acc.y += a.y;
+                        acc.z += a.z;
+                        acc.w += a.w;
+                    }
+                    store_row16(yt + (c0 + r) * g.ldy + p * 4, acc);
+                }
+            } else {
+                for (int idx = tid; idx < 32 * kCH; idx += nthreads) {
+                    const int r = idx / kCH, e = idx % kCH;
+                    if (r >= nrows || e >= cnt) continue;
+                    const int off = elem_offset(r, e);
+                    float acc = *reinterpret_cast<const float *>(t0 + off);
+                    for (int w = 1; w < g.W; ++w) acc += *reinterpret_cast<const float *>(t0 + w * wb + off);
+                    yt[(c0 + r) * g.ldy + e] = acc;
+                }
+            }
+        }
         __syncthreads();  // tile i is free: refill its stage
         if (i + kStagesX < nch) issue_load(i + kStagesX, stage);
         cp_async_commit();
@@ -405,31 +479,47 @@ bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constan
     }
     cp_async_wait<0>();
 
-    if (!live) return;
     if (warm_pass) {
-        for (int slot = 0; slot < g.bpw; ++slot) {
-            const int b = warp + slot * g.W;
-            if (b >= g.n_bands) break;
-            double *wsp = g.ws + (c * g.S + j);
+        if (live) {
+            for (int slot = 0; slot < g.bpw; ++slot) {
+                const int b = warp + slot * g.W;
+                if (b >= g.n_bands) break;
+                double *wsp = g.ws + (c * g.S + j);
 #pragma unroll
-            for (int k = 0; k < KB; ++k) {
-                const double2 s = stsm[(slot * KB + k) * 32 + lane];
-                wsp[((b * KB + k) * 2) * g.ws_stride] = s.x;
-                wsp[((b * KB + k) * 2 + 1) * g.ws_stride] = s.y;
+                for (int k = 0; k < KB; ++k) {
+                    const double2 s = stsm[(slot * KB + k) * 32 + lane];
+                    wsp[((b * KB + k) * 2) * g.ws_stride] = s.x;
+                    wsp[((b * KB + k) * 2 + 1) * g.ws_stride] = s.y;
+                }
             }
         }
         return;
     }
-    if (do_tail) {
+    if (do_tail) {  // CTA-uniform
         const bool from_true_state = n0 == 0;
-        for (int slot = 0; slot < g.bpw; ++slot) {
-            const int b = warp + slot * g.W;
-            if (b >= g.n_bands) break;
-            const double2 *st = stsm + slot * KB * 32;
-            if ((g.f64_mask >> b) & 1u)
-                band_tail<double, KB>(cd, g, b, g.band_id[b], c, n1, tail, from_true_state, st, lane);
-            else
-                band_tail<float, KB>(cd, g, b, g.band_id[b], c, n1, tail, from_true_state, st, lane);
+        float *partial = g.sum ? reinterpret_cast<float *>(otile) : nullptr;  // the output tile is free now
+        if (live) {
+            for (int slot = 0; slot < g.bpw; ++slot) {
+                const int b = warp + slot * g.W;
+                if (b >= g.n_bands) break;
+                const double2 *st = stsm + slot * KB * 32;
+                if ((g.f64_mask >> b) & 1u)
+                    band_tail<double, KB>(cd, g, b, g.band_id[b], c, n1, tail, from_true_state, st, lane, partial, slot == 0);
+                else
+                    band_tail<float, KB>(cd, g, b, g.band_id[b], c, n1, tail, from_true_state, st, lane, partial, slot == 0);
+            }
+        }
+        if (g.sum) {
+            __syncthreads();
+            if (warp == 0 && live) {
+                const unsigned char *t0 = base_sm + (kStagesX + 2) * kTileBytes;
+                const int wb = warp_bytes(g.bpw, KB);
+                for (int e = 0; e < tail; ++e) {
+                    float acc = reinterpret_cast<const float *>(t0)[e * 32 + lane];
+                    for (int w = 1; w < g.W; ++w) acc += reinterpret_cast<const float *>(t0 + w * wb)[e * 32 + lane];
+                    g.y[c * g.ldy + n1 - tail + e] = acc;
+                }
+            }
         }
     }
 }
@@ -477,14 +567,15 @@ bool bank_stack_tile_ok(int N, int Kb, int64_t C) {
 }
 
 int launch_bank_stack(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, int64_t ldb, const SosSection *sec,
-                      const int *band_id, const int64_t *warm_b, uint32_t f64_mask, int nb, int Kb, bool no_split, void *workspace,
-                      size_t workspace_bytes, double *state_x, double *state_y, cudaStream_t stream) {
+                      const int *band_id, const int64_t *warm_b, uint32_t f64_mask, int nb, int Kb, bool sum, bool no_split,
+                      void *workspace, size_t workspace_bytes, double *state_x, double *state_y, cudaStream_t stream) {
     StackGeom g{};
+    g.sum = sum ? 1 : 0;
     g.x = x;
     g.y = y;
     g.ldx = ldx;
     g.ldy = ldy;
-    g.ldb = ldb;
+    g.ldb = sum ? 0 : ldb;
     g.C = C;
     g.T = T;
     g.n_bands = nb;
@@ -519,7 +610,7 @@ int launch_bank_stack(const float *x, float *y, int64_t C, int64_t T, int64_t ld
     }
     const size_t esz = 4;
     g.vec_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0) && ((ldx * esz) % 16 == 0) &&
-               ((ldy * esz) % 16 == 0) && ((ldb * esz) % 16 == 0);
+               ((ldy * esz) % 16 == 0) && ((g.ldb * esz) % 16 == 0);
     switch (Kb) {
         case 1: return launch_stack_kb<1>(sec, g, seg, stream);
         case 2: return launch_stack_kb<2>(sec, g, seg, stream);

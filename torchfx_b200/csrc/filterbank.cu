@@ -487,7 +487,8 @@ int filterbank_device(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, int
 
     // STACK banks with enough channels: lanes = channels, per-band precision and warm-up (bank_stack.cu)
     if constexpr (sizeof(IO) == 4) {
-        if (mode == TFX_BANK_STACK && !(flags & TFX_NO_TILE) && bank_stack_tile_ok(N, Kb, C)) {
+        // (also SUM banks too large for the register-resident parallel topology above, up to 32 bands)
+        if ((mode == TFX_BANK_STACK || N <= 32) && !(flags & TFX_NO_TILE) && bank_stack_tile_ok(N, Kb, C)) {
             const uint32_t want = flags & TFX_PREC_MASK;
             TFX_REQUIRE(want == TFX_PREC_AUTO || want == TFX_PREC_F32 || want == TFX_PREC_F64, "filterbank: bad precision flag");
             for (int lo = 0; lo < N; lo += 32) {
@@ -506,8 +507,9 @@ int filterbank_device(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, int
                     band_id[b] = lo + b;
                     for (int k = 0; k < Kb; ++k) sec.push_back(pl.sec[k]);
                 }
-                rc = launch_bank_stack(x, y, C, T, ldx, ldy, ldb, sec.data(), band_id, warm_b, mask, nb, Kb, (flags & TFX_NO_SPLIT) != 0,
-                                       workspace, workspace_bytes, state_x, state_y, static_cast<cudaStream_t>(stream_v));
+                rc = launch_bank_stack(x, y, C, T, ldx, ldy, ldb, sec.data(), band_id, warm_b, mask, nb, Kb, mode == TFX_BANK_SUM,
+                                       (flags & TFX_NO_SPLIT) != 0, workspace, workspace_bytes, state_x, state_y,
+                                       static_cast<cudaStream_t>(stream_v));
                 if (rc != TFX_OK) return rc;
             }
             return TFX_OK;
