@@ -109,9 +109,11 @@ __device__ __forceinline__ void emit1(unsigned char *p, float y, int out_mode) {
         *reinterpret_cast<float *>(p) += y;
 }
 
+// lo[j] = byte offset of 16-byte column j (j < 8) of THIS lane's row inside a swizzled tile; column v lives at
+// lo[v & 7] + (v >> 3) * 4096, so the fully unrolled loops below address the tiles with immediates only.
 template <typename CT, int KB, int OUT>
 __device__ __forceinline__ void band_chunk(const StackCoef<KB> &cd, int b, const unsigned char *xin, unsigned char *out, double2 *st,
-                                           int lane, int cnt) {
+                                           int lane, int cnt, const int (&lo)[8]) {
     CT b0[KB], b1[KB], b2[KB], na1[KB], na2[KB], s1[KB], s2[KB];
 #pragma unroll
     for (int k = 0; k < KB; ++k) {
@@ -136,16 +138,18 @@ __device__ __forceinline__ void band_chunk(const StackCoef<KB> &cd, int b, const
         return static_cast<float>(v);
     };
     if (cnt == kCH) {
-        float4 a = *reinterpret_cast<const float4 *>(xin + col_offset(lane, 0));
-#pragma unroll 4
+        float4 a = *reinterpret_cast<const float4 *>(xin + lo[0]);
+#pragma unroll
         for (int v = 0; v < kNV; ++v) {
             // next vector first: the compiler cannot hoist a load over the store into the output tile
-            const float4 nxt = *reinterpret_cast<const float4 *>(xin + col_offset(lane, (v + 1) & (kNV - 1)));
+            constexpr int kMask = kNV - 1;
+            const int vn = (v + 1) & kMask;
+            const float4 nxt = *reinterpret_cast<const float4 *>(xin + lo[vn & 7] + (vn >> 3) * 4096);
             a.x = step(a.x);
             a.y = step(a.y);
             a.z = step(a.z);
             a.w = step(a.w);
-            emit4(out + col_offset(lane, v), a, OUT);
+            emit4(out + lo[v & 7] + (v >> 3) * 4096, a, OUT);
             a = nxt;
         }
     } else {
@@ -163,7 +167,7 @@ __device__ __forceinline__ void band_chunk(const StackCoef<KB> &cd, int b, const
 // the band's five DFMAs), rounds only the output.
 template <int KB, int OUT>
 __device__ __forceinline__ void band_chunk64(const StackCoef<KB> &cd, int b, const unsigned char *x64, unsigned char *out, double2 *st,
-                                             int lane, int cnt) {
+                                             int lane, int cnt, const int (&lo)[8]) {
     double b0[KB], b1[KB], b2[KB], na1[KB], na2[KB], s1[KB], s2[KB];
 #pragma unroll
     for (int k = 0; k < KB; ++k) {
@@ -187,17 +191,19 @@ __device__ __forceinline__ void band_chunk64(const StackCoef<KB> &cd, int b, con
         return static_cast<float>(v);
     };
     if (cnt == kCH) {
-        double2 a = *reinterpret_cast<const double2 *>(x64 + col_offset(lane, 0));
-#pragma unroll 4
+        double2 a = *reinterpret_cast<const double2 *>(x64 + lo[0]);
+#pragma unroll
         for (int v = 0; v < kNV; ++v) {
-            const double2 c = *reinterpret_cast<const double2 *>(x64 + col_offset(lane, 2 * v + 1));
-            const double2 nxt = *reinterpret_cast<const double2 *>(x64 + col_offset(lane, (2 * v + 2) & (2 * kNV - 1)));
+            constexpr int kMask = 2 * kNV - 1;
+            const int c1 = 2 * v + 1, c2 = (2 * v + 2) & kMask;
+            const double2 c = *reinterpret_cast<const double2 *>(x64 + lo[c1 & 7] + (c1 >> 3) * 4096);
+            const double2 nxt = *reinterpret_cast<const double2 *>(x64 + lo[c2 & 7] + (c2 >> 3) * 4096);
             float4 o;
             o.x = step(a.x);
             o.y = step(a.y);
             o.z = step(c.x);
             o.w = step(c.y);
-            emit4(out + col_offset(lane, v), o, OUT);
+            emit4(out + lo[v & 7] + (v >> 3) * 4096, o, OUT);
             a = nxt;
         }
     } else {
@@ -278,6 +284,10 @@ bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constan
     unsigned char *x64 = base_sm + kStagesX * kTileBytes;  // [32 x kCH] float64, same swizzle (2 * kNV columns)
     unsigned char *otile = base_sm + (kStagesX + 2) * kTileBytes + warp * warp_bytes(g.bpw, KB);
     double2 *stsm = reinterpret_cast<double2 *>(otile + kTileBytes);  // [slot * KB + k][lane]
+
+    int lo[8];  // this lane's swizzled column offsets (see band_chunk)
+#pragma unroll
+    for (int jc = 0; jc < 8; ++jc) lo[jc] = lane * 128 + ((jc ^ (lane & 7)) << 4);
 
     // ---- the item: channel group x time segment (CTA-uniform) -----------------------------------
     const bool warm_pass = g.warm > 0;
@@ -387,9 +397,9 @@ bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constan
                 if (n0 + base < start_b) continue;  // this band's window has not begun yet
                 if (live) {
                     if (is64)
-                        band_chunk64<KB, 0>(cd, b, x64, nullptr, st, lane, cnt);
+                        band_chunk64<KB, 0>(cd, b, x64, nullptr, st, lane, cnt, lo);
                     else
-                        band_chunk<float, KB, 0>(cd, b, tile, nullptr, st, lane, cnt);
+                        band_chunk<float, KB, 0>(cd, b, tile, nullptr, st, lane, cnt, lo);
                 }
                 continue;
             }
@@ -397,23 +407,23 @@ bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constan
                 if (live) {
                     if (slot == 0) {
                         if (is64)
-                            band_chunk64<KB, 1>(cd, b, x64, otile, st, lane, cnt);
+                            band_chunk64<KB, 1>(cd, b, x64, otile, st, lane, cnt, lo);
                         else
-                            band_chunk<float, KB, 1>(cd, b, tile, otile, st, lane, cnt);
+                            band_chunk<float, KB, 1>(cd, b, tile, otile, st, lane, cnt, lo);
                     } else {
                         if (is64)
-                            band_chunk64<KB, 2>(cd, b, x64, otile, st, lane, cnt);
+                            band_chunk64<KB, 2>(cd, b, x64, otile, st, lane, cnt, lo);
                         else
-                            band_chunk<float, KB, 2>(cd, b, tile, otile, st, lane, cnt);
+                            band_chunk<float, KB, 2>(cd, b, tile, otile, st, lane, cnt, lo);
                     }
                 }
                 continue;
             }
             if (live) {
                 if (is64)
-                    band_chunk64<KB, 1>(cd, b, x64, otile, st, lane, cnt);
+                    band_chunk64<KB, 1>(cd, b, x64, otile, st, lane, cnt, lo);
                 else
-                    band_chunk<float, KB, 1>(cd, b, tile, otile, st, lane, cnt);
+                    band_chunk<float, KB, 1>(cd, b, tile, otile, st, lane, cnt, lo);
             }
             __syncwarp();
             // ---- the band's [32 x 64] tile leaves as coalesced rows of y[gb] ---------------------
