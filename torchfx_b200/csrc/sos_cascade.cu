@@ -380,14 +380,16 @@ int launch_pass(const SosSection *sec, int k, const Geom &g, const Segmentation 
     }
 }
 
-// Kernel choice.  Measured on B200 (profiles/): the TMA tile path is capped near 4.6 TB/s by
-// the per-SM TMA request rate on DRAM-missing 128-byte rows, the cp.async path streams
-// faster but spends more issue slots per sample; TMA wins once the recurrence is heavy
-// (float64 or >= 6 sections).
+// Kernel choice.  The TMA tile path is capped near 4.6 TB/s by the per-SM TMA request rate on DRAM-missing
+// 128-byte rows (profiles/r1_experiments.md section 3).  While the cp.async tile kernel still read its tiles with
+// generic loads, TMA won the heavy cases (float64, K >= 6) and the dispatcher took it there; with LDS/STS tile
+// accesses the cp.async kernel is faster everywhere (1024 ch x 60 s, Gsamples/s, tile vs TMA: f64 K=4 625 vs 487,
+// f64 K=6 466 vs 366, f32 K=6 694 vs 527, f32 K=8 525 vs 489), so TMA now runs only on request (TFX_FORCE_TMA).
 bool want_tma(uint32_t flags, uint32_t prec, int k) {
+    (void)prec;
+    (void)k;
     if (flags & TFX_NO_TMA) return false;
-    if (flags & TFX_FORCE_TMA) return true;
-    return prec == TFX_PREC_F64 || k >= 6;
+    return (flags & TFX_FORCE_TMA) != 0;
 }
 
 int64_t stream_capacity() { return static_cast<int64_t>(sm_count()) * kWarpsPerSm * 32; }
