@@ -315,8 +315,13 @@ struct Cascade<ParMixed<N64, KB>, K> {
     }
 };
 
+// Register budget: float64-heavy instantiations with more than TFX_T_HEAVY_K sections run at half the residency
+// (up to 255 registers); the others are held to 65536 / (13 x 32) registers so that 13 warps per SM stay resident.
+#ifndef TFX_T_HEAVY_K
+#define TFX_T_HEAVY_K 4
+#endif
 template <typename IO, typename CT, int K>
-__global__ void __launch_bounds__(kWarps * 32, CtTraits<CT>::heavy ? (kCtasPerSm + 1) / 2 : kCtasPerSm)
+__global__ void __launch_bounds__(kWarps * 32, (CtTraits<CT>::heavy && K > TFX_T_HEAVY_K) ? (kCtasPerSm + 1) / 2 : kCtasPerSm)
 sos_tile_kernel(const __grid_constant__ SosCoef<typename CtTraits<CT>::Coef, K> cf, const __grid_constant__ SosCoefD<K> cd,
                 const __grid_constant__ TileGeom g) {
     using Store = typename CtTraits<CT>::Store;
