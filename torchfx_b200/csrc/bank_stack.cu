@@ -17,6 +17,9 @@
 //   * band states live in shared memory between tiles ([slot][section][lane] double2, 2 LDS + 2 STS
 //     per band per 64 samples) and coefficients come from the constant bank, so registers do not
 //     limit the number of bands and all control flow and addressing is warp-uniform.
+// SUM mode (`f1 + f2 + ...` with 9 .. 32 children, filter/__base.py:1019-1026): the same CTA, but a warp ADDS its
+// bands into its tile (slot order), the warps' partial tiles are added in warp order after a barrier and the
+// CTA stores one tile of y[C, T] per input tile -- 8 B per channel-sample whatever N is.
 // DF1 state contract ([N, Kb, C, 2] float64, in place), time segmentation and warm-up launch are
 // those of the other kernels (sos_plan.cpp); the last two samples of a channel run through a
 // scalar epilogue that records each section's DF1 history.

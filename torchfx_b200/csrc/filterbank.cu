@@ -4,6 +4,11 @@
 // n_bands native calls + torch.stack) and ParallelFilterCombination.forward
 // (filter/__base.py:1019-1026, N native calls + N temporaries + N adds).
 //
+// Dispatch (filterbank_device): with enough channels to fill 32-lane groups and float32 I/O the bank runs on the
+// lanes = channels kernels -- SUM banks of <= 8 sections on the cascade tile kernel's parallel topology
+// (bank_tile.cu, bank_tile_mixed.cu), STACK banks and larger SUM banks on bank_stack_kernel (bank_stack.cu).
+// Few channels, float64 I/O and SUM banks of more than 32 bands take the kernel in THIS file:
+//
 // Layout: BAND PER LANE.  A warp serves 32/LB streams (stream = channel x time segment,
 // exactly as in sos_cascade.cu); within a stream LB = next_pow2(N) lanes each own one band:
 // the band's coefficients and DF2T state live in that lane's registers.  Per 256-byte input
