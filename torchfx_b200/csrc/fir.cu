@@ -606,24 +606,39 @@ __global__ void __launch_bounds__(512, 1) fir_mac_kernel(const float2 *__restric
         // rows needed: j + (P-1) - p for j in [j0, j0 + kMacBlocks), p in [32pc, 32pc+npl)
         const int row_lo = it.j0 + (P - 1) - (it.pc * kMacPc + kMacPc - 1);
         const int r_first = kMacPc - npl;  // local rows below this belong to partitions that are not run
-        for (int i = threadIdx.x + r_first * 32; i < kMacRows * 32; i += 512) {
-            const int r = i >> 5, q = i & 31;  // 32 16-byte pieces per 64-bin row
-            const int row = row_lo + r;
-            const bool ok = row >= 0 && row < nvalid;
-            int slot = ring0 + row;
-            slot = slot >= nrows ? slot - nrows : slot;
-            cp_async16_zfill(buf + r * kMacBins + 2 * q, Zp + (ok ? static_cast<int64_t>(slot) * n_fft : 0) + 2 * q, ok);
+        // Thread (w, q) copies 16-byte piece q of local rows r_first + w, + 16, ...: ring slot, source pointer and
+        // shared-memory address advance by constants (the staging loop used to redo the ring arithmetic and a
+        // 64-bit multiply per row -- integer work that competes with the FFMAs for the FMA pipe).
+        const int q = threadIdx.x & 31;
+        int r = (threadIdx.x >> 5) + r_first;
+        int row = row_lo + r;
+        int slot = ring0 + row;  // may be negative while row < 0: never dereferenced then
+        if (slot >= nrows) slot -= nrows;
+        const float2 *src = Zp + static_cast<int64_t>(slot) * n_fft + 2 * q;
+        const int64_t step = static_cast<int64_t>(16) * n_fft, wrap = static_cast<int64_t>(nrows) * n_fft;
+        float2 *dst = buf + r * kMacBins + 2 * q;
+#pragma unroll 2
+        for (; r < kMacRows; r += 16) {
+            const bool ok = static_cast<unsigned>(row) < static_cast<unsigned>(nvalid);
+            cp_async16_zfill(dst, ok ? src : Zp, ok);
+            row += 16;
+            slot += 16;
+            src += step;
+            if (slot >= nrows) {
+                slot -= nrows;
+                src -= wrap;
+            }
+            dst += 16 * kMacBins;
         }
         float2 *hb = buf + kMacRows * kMacBins;
         for (int i = threadIdx.x; i < npl * 32; i += 512) {
-            const int pl = i >> 5, q = i & 31;
+            const int pl = i >> 5;
             const int p = it.pc * kMacPc + pl;
             const bool ok = p < P;
             cp_async16_zfill(hb + pl * kMacBins + 2 * q, H + (ok ? static_cast<int64_t>(p) * n_fft : 0) + it.f0 + 2 * q, ok);
         }
         cp_async_commit();
     };
-
 #endif
     float2 acc[R];
     // this CTA's work: tiles blockIdx.x, blockIdx.x + gridDim.x, ...; within a tile chunks 0..nchunks-1
