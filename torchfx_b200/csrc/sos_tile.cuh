@@ -210,7 +210,7 @@ struct Cascade<Par<CT, KB>, K> {
             s1[k] = fma_rn(cf.na1[k], y, fma_rn(cf.b1[k], v, s2[k]));
             s2[k] = fma_rn(cf.na2[k], y, cf.b2[k] * v);
             v = y;
-            if (k % KB == KB - 1) acc += static_cast<IO>(v);
+            if (k % KB == KB - 1) acc = (k == KB - 1) ? static_cast<IO>(v) : acc + static_cast<IO>(v);  // 0 + y0 == y0
         }
         return acc;
     }
@@ -231,7 +231,7 @@ struct Cascade<Par<CT, KB>, K> {
             hy[k][1] = hy[k][0];
             hy[k][0] = y;
             v = y;
-            if (k % KB == KB - 1) acc += static_cast<IO>(v);
+            if (k % KB == KB - 1) acc = (k == KB - 1) ? static_cast<IO>(v) : acc + static_cast<IO>(v);  // 0 + y0 == y0
         }
         return acc;
     }
