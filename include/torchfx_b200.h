@@ -67,6 +67,9 @@ extern "C" {
                               /* B200, kept for A/B timing and tests                  */
 #define TFX_NO_TILE     0x40u /* never take the channel-tile kernel (lanes = channels); use the    */
                               /* stream-per-lane kernel even for many channels (A/B, tests)       */
+#define TFX_FORCE_TILE  0x80u /* filterbank: take the lanes = channels kernel (bank_stack) even when */
+                              /* its grid would leave most SMs idle and the library would pick the   */
+                              /* band-per-lane kernel (small C x T; A/B, tests)                      */
 #define TFX_NO_SPLIT    0x4u /* never split a channel in time (one sequential stream per     */
                              /* channel; exact for unstable filters; used by tests)          */
 

@@ -200,6 +200,7 @@ def test_stack_tile_vs_oracle(n_bands, C):
     mk = lambda: [fx.filter.BiquadBPF(150.0 * (1.12 ** i), 1.414, 48000) for i in range(n_bands)]
     filters = mk()
     bank = SosBank(filters, mode="stack")
+    bank.flags = _native.TFX_FORCE_TILE  # this shape is too small to fill the GPU: the default dispatch would take the band-per-lane kernel
     before = _native.kernel_launches()
     y = bank(torch.from_numpy(x).to(DEV)).cpu().numpy()
     assert _native.kernel_launches() - before <= 2 * ((n_bands + 31) // 32)
@@ -207,7 +208,7 @@ def test_stack_tile_vs_oracle(n_bands, C):
     want = oracle.filterbank_stack(x, sos)
     assert y.shape == want.shape == (n_bands, C, T)
     assert max(rel_to_max(y[b], want[b]) for b in range(n_bands)) < TOL
-    for flags in (_native.TFX_NO_TILE, _native.TFX_NO_SPLIT):
+    for flags in (_native.TFX_NO_TILE, _native.TFX_NO_SPLIT | _native.TFX_FORCE_TILE, 0):
         other = SosBank(mk(), mode="stack")
         other.flags = flags
         y2 = other(torch.from_numpy(x).to(DEV)).cpu().numpy()
@@ -235,6 +236,7 @@ def test_stack_tile_multi_section_chunked(precision):
 
     filters = make()
     bank = SosBank(filters, mode="stack")
+    bank.flags = _native.TFX_FORCE_TILE
     xt = torch.from_numpy(x).to(DEV)
     old = _ops.get_default_precision()
     _ops.set_default_precision(precision)
@@ -337,6 +339,7 @@ def test_sum_many_bands_vs_oracle(n, kb, C):
 
     filters = mk()
     bank = SosBank(filters, mode="sum")
+    bank.flags = _native.TFX_FORCE_TILE
     xt = torch.from_numpy(x).to(DEV)
     before = _native.kernel_launches()
     y = torch.cat([bank(xt[:, :1]), bank(xt[:, 1:25001]), bank(xt[:, 25001:])], dim=1).cpu().numpy()
@@ -378,3 +381,33 @@ def test_sum_8192_lanes_linearity():
         f.compute_coefficients()
     want = oracle.filterbank_sum(x1[sel].cpu().numpy(), np.stack([f._sos.numpy() for f in filters]))
     assert rel_to_max(y1[sel].cpu().numpy(), want) < TOL
+
+
+@pytest.mark.parametrize("C,T", [(32, 700000), (128, 480000), (64, 200000)])
+def test_stack_band_split_over_ctas(C, T):
+    """Few channel groups: the 32 bands of a LogFilterBank are split over up to 4 CTAs per (group, segment) so the grid
+    still fills the GPU (C = 32 is the 8-GPU shard of config 5).  Default dispatch; oracle parity on 3 channels and on
+    the carried state; the forced single-split / band-per-lane paths agree."""
+    from torchfx_b200.filter._sosbank import SosBank
+
+    g = torch.Generator(device=DEV).manual_seed(C + T)
+    x = 0.1 * torch.randn(C, T, device=DEV, generator=g)
+    bank = fx.filter.LogFilterBank(n_bands=32, f_min=20.0, f_max=20000.0, fs=48000)
+    y = bank(x)
+    assert y.shape == (32, C, T)
+    sel = [0, C // 2, C - 1]
+    bank.compute_coefficients()
+    sos = np.stack([f._sos.numpy() for f in bank.filters])
+    xs = x[sel].cpu().numpy()
+    want = oracle.filterbank_stack(xs, sos)
+    got = y[:, sel].cpu().numpy()
+    assert max(rel_to_max(got[b], want[b]) for b in range(32)) < TOL
+    for i in (0, 17, 31):
+        _, wsx, wsy = oracle.sos_cascade(xs, sos[i])
+        np.testing.assert_allclose(bank.filters[i]._state_y[:, sel].cpu().numpy(), wsy, rtol=1e-3, atol=1e-5 * np.abs(wsy).max())
+    mk = lambda: [fx.filter.BiquadBPF(float(f.cutoff), 1.414, 48000) for f in bank.filters]
+    other = SosBank(mk(), mode="stack")
+    other.flags = _native.TFX_NO_TILE
+    y2 = other(x)
+    err = ((y2 - y).abs().amax(dim=(1, 2)) / y.abs().amax(dim=(1, 2))).max().item()
+    assert err < 5e-6

@@ -26,6 +26,7 @@ LIB_PATH = os.environ.get("TFX_B200_LIB") or os.path.join(os.path.dirname(os.pat
 TFX_OK = 0
 TFX_EINVAL, TFX_ENODEVICE, TFX_ECUDA, TFX_EWORKSPACE, TFX_ENOMEM = -1, -2, -3, -4, -5
 TFX_PREC_AUTO, TFX_PREC_F32, TFX_PREC_F64, TFX_NO_SPLIT, TFX_NO_TMA, TFX_FORCE_TMA, TFX_PACKED, TFX_NO_TILE = 0, 1, 2, 4, 8, 16, 32, 64
+TFX_FORCE_TILE = 128
 TFX_BANK_STACK, TFX_BANK_SUM = 0, 1
 TFX_FIR_AUTO, TFX_FIR_DIRECT, TFX_FIR_OLS = 0, 1, 2
 TFX_SOS_MAX_K = 64

@@ -71,6 +71,8 @@ struct StackGeom {
     int bpw;            // band slots per warp = ceil(n_bands / W)
     uint32_t f64_mask;  // bit b: band b runs the float64 recurrence
     int vec_ok;
+    int nsplit;       // STACK: the bands are split over nsplit CTAs per (channel group, segment) -- more CTAs when C*T is small
+    int bps;          // bands per split
     int sum;          // 1: SUM mode -- the bands are added (warp partials in slot order, then warps in order) into y[C, T]
     int band_id[32];  // global band index of local band b (y plane and state block)
     int warm_b[32];   // warm-up samples band b needs (multiple of 64, <= warm)
@@ -397,7 +399,10 @@ bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constan
 
     // ---- the item: channel group x time segment (CTA-uniform) -----------------------------------
     const bool warm_pass = g.warm > 0;
-    const int64_t item = blockIdx.x;
+    int64_t item = blockIdx.x;
+    const int b_first = static_cast<int>(item % g.nsplit) * g.bps;  // this CTA's bands: [b_first, b_first + nb_cta)
+    item /= g.nsplit;
+    const int nb_cta = min(g.bps, g.n_bands - b_first);
     int64_t grp, j, n0, n1;
     if (warm_pass) {
         const int64_t sm1 = g.S - 1;
@@ -422,8 +427,9 @@ bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constan
 
     // ---- start states of my bands -> shared memory ------------------------------------------------
     for (int slot = 0; slot < g.bpw; ++slot) {
-        const int b = warp + slot * g.W;
-        if (b >= g.n_bands) break;
+        const int bl = warp + slot * g.W;
+        if (bl >= nb_cta) break;
+        const int b = b_first + bl;
         const int64_t gb = g.band_id[b];
         // absolute sample at which band b starts in this launch: the segment start, or (warm-up) its own window
         const int64_t start_b = warm_pass ? max(n1 - static_cast<int64_t>(g.warm_b[b]), static_cast<int64_t>(0)) : n0;
@@ -483,7 +489,7 @@ bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constan
         const int64_t base = i * kCH;
         const int cnt = static_cast<int>(min(len - base, static_cast<int64_t>(kCH)));
 
-        if (g.f64_mask != 0u) {  // CTA-uniform: float64 copy of the tile for the float64 bands
+        if (((g.f64_mask >> b_first) & ((nb_cta >= 32 ? 0u : (1u << nb_cta)) - 1u)) != 0u) {  // CTA-uniform: float64 copy of the tile for this CTA's float64 bands
             for (int idx = tid; idx < 32 * kNV; idx += nthreads) {
                 const int r = idx / kNV, p = idx % kNV;
                 const float4 a = *reinterpret_cast<const float4 *>(tile + col_offset(r, p));
@@ -494,15 +500,16 @@ bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constan
         }
 
         for (int slot = 0; slot < g.bpw; ++slot) {
-            const int b = warp + slot * g.W;
-            if (b >= g.n_bands) break;
+            const int bl = warp + slot * g.W;
+            if (bl >= nb_cta) break;
+            const int b = b_first + bl;
             double2 *st = stsm + slot * KB * 32;
             const bool is64 = (g.f64_mask >> b) & 1u;
             // ---- two bands at once where no per-band output tile is needed (warm-up, SUM) ---------------
             if (warm_pass || g.sum) {
                 const int bn = b + g.W;
                 constexpr bool kPair64 = KB <= 2;  // two float64 bands of 3+ sections do not fit the register budget
-                bool pair = slot + 1 < g.bpw && bn < g.n_bands && (((g.f64_mask >> bn) & 1u) != 0u) == is64 && (kPair64 || !is64);
+                bool pair = slot + 1 < g.bpw && bl + g.W < nb_cta && (((g.f64_mask >> bn) & 1u) != 0u) == is64 && (kPair64 || !is64);
                 if (pair && warm_pass) {  // both windows must have begun
                     const int64_t sa = max(n1 - static_cast<int64_t>(g.warm_b[b]), static_cast<int64_t>(0));
                     const int64_t sb = max(n1 - static_cast<int64_t>(g.warm_b[bn]), static_cast<int64_t>(0));
@@ -632,8 +639,9 @@ bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constan
     if (warm_pass) {
         if (live) {
             for (int slot = 0; slot < g.bpw; ++slot) {
-                const int b = warp + slot * g.W;
-                if (b >= g.n_bands) break;
+                const int bl = warp + slot * g.W;
+                if (bl >= nb_cta) break;
+                const int b = b_first + bl;
                 double *wsp = g.ws + (c * g.S + j);
 #pragma unroll
                 for (int k = 0; k < KB; ++k) {
@@ -650,8 +658,9 @@ bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constan
         float *partial = g.sum ? reinterpret_cast<float *>(otile) : nullptr;  // the output tile is free now
         if (live) {
             for (int slot = 0; slot < g.bpw; ++slot) {
-                const int b = warp + slot * g.W;
-                if (b >= g.n_bands) break;
+                const int bl = warp + slot * g.W;
+                if (bl >= nb_cta) break;
+                const int b = b_first + bl;
                 const double2 *st = stsm + slot * KB * 32;
                 if ((g.f64_mask >> b) & 1u)
                     band_tail<double, KB>(cd, g, b, g.band_id[b], c, n1, tail, from_true_state, st, lane, partial, slot == 0);
@@ -700,16 +709,50 @@ int launch_stack_kb(const SosSection *sec, StackGeom g, const Segmentation &seg,
     if (seg.S > 1) {
         StackGeom gw = g;
         gw.warm = seg.warm;
-        kern<<<static_cast<unsigned>(G * (seg.S - 1)), g.W * 32, smem, stream>>>(cd, gw);
+        kern<<<static_cast<unsigned>(G * (seg.S - 1) * g.nsplit), g.W * 32, smem, stream>>>(cd, gw);
         TFX_CHECK_LAUNCH("bank_stack_kernel(warm-up)");
     }
     g.warm = 0;
-    kern<<<static_cast<unsigned>(G * seg.S), g.W * 32, smem, stream>>>(cd, g);
+    kern<<<static_cast<unsigned>(G * seg.S * g.nsplit), g.W * 32, smem, stream>>>(cd, g);
     TFX_CHECK_LAUNCH("bank_stack_kernel");
     return TFX_OK;
 }
 
+
+// How one launch is cut: time segments (sos_plan.cpp) and, for STACK banks over few channels / short signals, the
+// bands over up to 4 CTAs per (channel group, segment) so that the grid still fills the GPU (x is re-read per split:
+// 4/N of the output traffic each).  items = CTAs of the main launch, resident = CTAs the GPU holds at once.
+struct StackPlan {
+    int nsplit, bps, W, bpw;
+    Segmentation seg;
+    int64_t items, resident;
+};
+StackPlan plan_stack(int64_t C, int64_t T, int nb, int Kb, int64_t warm_max, bool sum, bool no_split) {
+    const int64_t G = (C + 31) / 32, lanes = G * 32;
+    StackPlan best{};
+    for (int ns = 1; ns <= (sum ? 1 : 4) && ns <= nb; ns *= 2) {
+        StackPlan p{};
+        p.bps = (nb + ns - 1) / ns;
+        p.nsplit = (nb + p.bps - 1) / p.bps;
+        p.W = std::min(kMaxWarps, p.bps);
+        p.bpw = (p.bps + p.W - 1) / p.W;
+        p.resident = static_cast<int64_t>(sm_count()) * ctas_per_sm(p.W, p.bpw, Kb);
+        const int64_t s_cap = std::max<int64_t>(p.resident / (G * p.nsplit), 1);
+        p.seg = choose_segmentation(lanes, T, warm_max, s_cap * lanes, no_split);
+        p.items = G * p.seg.S * p.nsplit;
+        if (ns == 1 || p.items > best.items) best = p;
+        if (best.items * 10 >= best.resident * 9) break;  // (nearly) a full wave of CTAs: enough
+    }
+    return best;
+}
+
 }  // namespace
+
+bool bank_stack_worthwhile(int64_t C, int64_t T, int nb, int Kb, int64_t warm_max, bool sum, bool no_split) {
+    const int64_t wa = warm_max < 0 ? 0 : (warm_max + kCH - 1) / kCH * kCH;
+    const StackPlan p = plan_stack(C, T, nb, Kb, wa, sum, no_split || warm_max < 0);
+    return p.items * 4 >= p.resident;  // below a quarter of a wave the band-per-lane kernel fills the GPU better
+}
 
 bool bank_stack_tile_ok(int N, int Kb, int64_t C) {
     const int64_t G = (C + 31) / 32;
@@ -729,8 +772,6 @@ int launch_bank_stack(const float *x, float *y, int64_t C, int64_t T, int64_t ld
     g.C = C;
     g.T = T;
     g.n_bands = nb;
-    g.W = std::min(kMaxWarps, nb);
-    g.bpw = (nb + g.W - 1) / g.W;
     g.f64_mask = f64_mask;
     g.state_x = state_x;
     g.state_y = state_y;
@@ -744,9 +785,12 @@ int launch_bank_stack(const float *x, float *y, int64_t C, int64_t T, int64_t ld
         warm_max = std::max(warm_max, wa);
     }
     if (warm_max > (int64_t(1) << 30)) no_split = true;
-    const int64_t lanes = (C + 31) / 32 * 32;
-    const int64_t capacity = static_cast<int64_t>(sm_count()) * ctas_per_sm(g.W, g.bpw, Kb) * 32;
-    const Segmentation seg = choose_segmentation(lanes, T, warm_max, capacity, no_split);
+    const StackPlan pl = plan_stack(C, T, nb, Kb, warm_max, sum, no_split);
+    g.nsplit = pl.nsplit;
+    g.bps = pl.bps;
+    g.W = pl.W;
+    g.bpw = pl.bpw;
+    const Segmentation seg = pl.seg;
     g.S = seg.S;
     g.Lseg = seg.Lseg;
     g.ws = static_cast<double *>(workspace);

@@ -27,6 +27,9 @@ int launch_bank_sum_tile_mixed(const float *x, float *y, int64_t C, int64_t T, i
 // precision (bit b of f64_mask) and per-band warm-up lengths (warm_b[b] < 0: band does not decay).
 bool bank_stack_tile_ok(int N, int Kb, int64_t C);
 int64_t bank_stack_max_streams();  // upper bound of C * S (workspace sizing)
+// False when this shape would leave most SMs idle (few channel groups x few time segments, even with the bands
+// split over 4 CTAs): the band-per-lane kernel then fills the GPU better.  warm_max: longest band warm-up (< 0: none decays).
+bool bank_stack_worthwhile(int64_t C, int64_t T, int nb, int Kb, int64_t warm_max, bool sum, bool no_split);
 // sum = true: the bands are added into y[C, T] (`f1 + f2 + ...` with more than 8 sections in total) instead of stacked.
 int launch_bank_stack(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, int64_t ldb, const SosSection *sec,
                       const int *band_id, const int64_t *warm_b, uint32_t f64_mask, int nb, int Kb, bool sum, bool no_split,

@@ -493,7 +493,16 @@ int filterbank_device(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, int
     // STACK banks with enough channels: lanes = channels, per-band precision and warm-up (bank_stack.cu)
     if constexpr (sizeof(IO) == 4) {
         // (also SUM banks too large for the register-resident parallel topology above, up to 32 bands)
-        if ((mode == TFX_BANK_STACK || N <= 32) && !(flags & TFX_NO_TILE) && bank_stack_tile_ok(N, Kb, C)) {
+        bool stack_kernel = (mode == TFX_BANK_STACK || N <= 32) && !(flags & TFX_NO_TILE) && bank_stack_tile_ok(N, Kb, C);
+        if (stack_kernel && !(flags & TFX_FORCE_TILE)) {  // enough (channel group x segment x band split) items to fill the GPU?
+            int64_t warm_max = 0;
+            for (int b = 0; b < std::min(N, 32); ++b) {
+                const int64_t w = plans[b]->passes[0].warm_f32;
+                warm_max = (w < 0 || warm_max < 0) ? -1 : std::max(warm_max, w);
+            }
+            stack_kernel = bank_stack_worthwhile(C, T, std::min(N, 32), Kb, warm_max, mode == TFX_BANK_SUM, (flags & TFX_NO_SPLIT) != 0);
+        }
+        if (stack_kernel) {
             const uint32_t want = flags & TFX_PREC_MASK;
             TFX_REQUIRE(want == TFX_PREC_AUTO || want == TFX_PREC_F32 || want == TFX_PREC_F64, "filterbank: bad precision flag");
             for (int lo = 0; lo < N; lo += 32) {
