@@ -1,0 +1,46 @@
+"""pytest plugin: make ``import torchfx`` resolve to ``torchfx_b200`` so the reference's own
+hot-path test files run unmodified against this package.
+
+Loaded with ``-p _refsuite_plugin`` (tests/ on PYTHONPATH) by tests/test_reference_suite.py in a child
+pytest process; nothing in the product imports it.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+_SUBMODULES = {
+    "_ops": "_ops",
+    "effect": "effect",
+    "wave": "wave",
+    "chain": "chain",
+    "typing": "typing",
+    "filter": "filter",
+    "filter.__base": "filter._base",  # the reference's private module name (tests/test_filter_base.py:18)
+    "filter.biquad": "filter.biquad",
+    "filter.filterbank": "filter.filterbank",
+    "filter.fir": "filter.fir",
+    "filter.fused": "filter.fused",
+    "filter.iir": "filter.iir",
+    "filter.utils": "filter.utils",
+    "filter._fftconv": "filter._fftconv",
+}
+
+
+def _install() -> None:
+    pkg = importlib.import_module("torchfx_b200")
+    sys.modules["torchfx"] = pkg
+    for ref_name, ours in _SUBMODULES.items():
+        sys.modules[f"torchfx.{ref_name}"] = importlib.import_module(f"torchfx_b200.{ours}")
+
+
+_install()
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "benchmark: reference marker (unused here)")

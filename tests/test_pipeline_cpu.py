@@ -95,18 +95,38 @@ def test_gain_folding_rules():
     torch.manual_seed(4)
     x = torch.randn(2, 4000)
     lo, hi = LoButterworth(3000, order=2), HiButterworth(100, order=2)
-    # leading / trailing / dB gains fold; a clamping gain and a single-IIR run do not
-    w = fx.Wave(x, FS) | fx.Gain(2.0) | lo | fx.Gain(-6.0, gain_type="db") | hi | fx.Gain(0.25)
+    lo2, hi2 = LoButterworth(2500, order=2), HiButterworth(60, order=2)
+    # leading / trailing / dB gains fold into runs of >= 2 filters and merge the runs around them
+    w = fx.Wave(x, FS) | fx.Gain(2.0) | lo | hi | fx.Gain(-6.0, gain_type="db") | lo2 | hi2 | fx.Gain(0.25)
     plan = w._plan()
     assert [type(m).__name__ for m in plan] == ["FusedSOSCascade"]
     g = 2.0 * 10 ** (-6.0 / 20) * 0.25
-    assert abs(plan[0].gain - g) < 1e-12
-    ref = _sequential(x, [lo, hi]) * g
+    assert abs(plan[0].gain - g) < 1e-12 and plan[0]._num_sections == 4
+    ref = _sequential(x, [lo, hi, lo2, hi2]) * g
     np.testing.assert_allclose(w.ys.numpy(), ref, atol=2e-6)
+    # a clamping gain never folds
     w = fx.Wave(x, FS) | lo | fx.Gain(4.0, clamp=True) | hi
     assert [type(m).__name__ for m in w._plan()] == ["LoButterworth", "Gain", "HiButterworth"]
     w = fx.Wave(x, FS) | fx.Gain(0.5) | LoButterworth(3000, order=2)
     assert [type(m).__name__ for m in w._plan()] == ["Gain", "LoButterworth"]
+    # a lone filter is a stateful step in the reference (wave.py:227-233): it is never absorbed, and it separates
+    w = fx.Wave(x, FS) | lo | hi | fx.Gain(0.5) | lo2
+    assert [type(m).__name__ for m in w._plan()] == ["FusedSOSCascade", "LoButterworth"]
+    w = fx.Wave(x, FS) | lo | fx.Gain(0.5) | hi
+    assert [type(m).__name__ for m in w._plan()] == ["LoButterworth", "Gain", "HiButterworth"]
+
+
+def test_gain_between_lone_filters_keeps_their_state():
+    """``Wave(chunk) | lp | Gain | hp`` per chunk must continue the stream as in the reference --
+    lp and hp run as the modules themselves and carry their DF1 state between materialisations."""
+    torch.manual_seed(5)
+    x = torch.randn(2, 6000)
+    lp, hp = LoButterworth(3000, order=4), HiButterworth(100, order=2)
+    g = fx.Gain(0.5)
+    pieces = [(fx.Wave(x[:, a:b], FS) | lp | g | hp).ys for a, b in ((0, 2500), (2500, 6000))]
+    assert lp._state_x is not None and hp._state_x is not None
+    ref = sps.sosfilt(hp._sos.numpy(), 0.5 * sps.sosfilt(lp._sos.numpy(), x.numpy().astype(np.float64), axis=-1), axis=-1)
+    np.testing.assert_allclose(torch.cat(pieces, dim=1).numpy(), ref, atol=2e-6)
 
 
 def test_fused_construction_errors_and_from_chain():

@@ -1,0 +1,56 @@
+"""The reference's own hot-path test files, run unmodified against this package.
+
+SURVEY.md section 4 ("reused as the parity suite") / section 7 step 1: ``import torchfx`` is aliased to
+``torchfx_b200`` (tests/_refsuite_plugin.py) and the 13 files listed in
+tests/_refsuite_fetch.py are executed in a child pytest.  On the CPU box every CUDA case skips
+itself; under ``-m gpu`` the same files run again on the B200, where
+``test_cuda_kernels.py`` (reference tests/test_cuda_kernels.py:35-184) and the CUDA-parametrised
+cases exercise the CUDA kernels through the reference's own assertions.
+"""
+from __future__ import annotations
+
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import _refsuite_fetch as fetch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(files: list[str]) -> tuple[int, dict[str, int], str]:
+    d = fetch.tests_dir()
+    if d is None:
+        pytest.skip("reference test files not available (neither /root/reference nor baseline/_ref/tests)")
+    paths = [os.path.join(d, f) for f in files]
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, os.path.join(ROOT, "tests"), os.environ.get("PYTHONPATH", "")]))
+    cmd = [sys.executable, "-m", "pytest", "-c", os.devnull, "--rootdir", d, "-q", "-p", "_refsuite_plugin",
+           "-p", "no:cacheprovider", "--import-mode=importlib", *paths]
+    out = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    text = out.stdout + out.stderr
+    counts = {k: int(n) for n, k in re.findall(r"(\d+) (passed|failed|skipped|error|errors)", text.splitlines()[-1] if text else "")}
+    return out.returncode, counts, text
+
+
+def test_reference_hot_path_files_cpu():
+    """All 13 files on CPU tensors (CUDA cases skip themselves): the reference's 206 + test_fftconv."""
+    rc, counts, text = _run(list(fetch.HOT_PATH_FILES))
+    assert rc == 0, text[-4000:]
+    assert counts.get("failed", 0) == 0 and counts.get("error", 0) + counts.get("errors", 0) == 0, text[-4000:]
+    if not torch.cuda.is_available():
+        assert counts.get("passed", 0) >= 206, counts
+
+
+@pytest.mark.gpu
+def test_reference_hot_path_files_cuda():
+    """Same files on the B200: nothing may skip for lack of CUDA, test_cuda_kernels.py runs in full."""
+    rc, counts, text = _run(list(fetch.HOT_PATH_FILES))
+    assert rc == 0, text[-4000:]
+    assert counts.get("failed", 0) == 0, text[-4000:]
+    assert counts.get("passed", 0) >= 220, counts
+    rc, counts, text = _run(["test_cuda_kernels.py"])
+    assert rc == 0 and counts.get("skipped", 0) == 0 and counts.get("passed", 0) >= 20, text[-4000:]

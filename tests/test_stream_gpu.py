@@ -31,7 +31,11 @@ def test_fused_stream_matches_oracle_and_carries_state(pinned):
     y = proc.process_tensor(x, fs=FS)
     fused = proc._fused_cascade()
     assert fused is not None and y.shape == x.shape and not y.is_cuda and y.is_pinned() == pinned
-    ref, _, _ = oracle.sos_cascade(x.numpy(), fused._sos.numpy())
+    # independent oracle for the folded gain: cascade -> x g -> cascade, each filter's OWN coefficients
+    mid, _, _ = oracle.sos_cascade(x.numpy(), effects[0]._sos.numpy())
+    mid = (mid.astype(np.float64) * 0.5)
+    ref, _, _ = oracle.sos_cascade(mid, np.vstack([effects[2]._sos.numpy(), effects[3]._sos.numpy()]))
+    assert fused.gain == 0.5 and fused._num_sections == 2 + 2 + 1
     assert rel_to_max(y.numpy(), ref) < 1e-5
     # two halves with carried state == one call
     proc.reset_state()

@@ -34,8 +34,11 @@ class FX(nn.Module, abc.ABC):
 
 
 class Gain(FX):
-    """Amplitude / dB / power gain (reference effect.py:261-383).  Breaks an IIR run in
-    ``Wave._materialize`` exactly as in the reference (tests/test_chain_fusion.py:102-120)."""
+    """Amplitude / dB / power gain (reference effect.py:261-383).  In the reference a Gain always
+    breaks an IIR run in ``Wave._materialize`` (tests/test_chain_fusion.py:102-120); here a
+    non-clamping Gain next to a fused run of >= 2 filters is folded into that run's
+    coefficients (``torchfx_b200.wave.FOLD_GAIN``), which leaves the results and the set of
+    statefully-run modules unchanged; next to a lone filter it stays a step of its own."""
 
     def __init__(self, gain: float, gain_type: str = "amplitude", clamp: bool = False) -> None:
         super().__init__()

@@ -14,6 +14,29 @@ from torch import Tensor
 from .fir import fir_causal
 
 
+def pad_to(tensor: Tensor, target_length: int) -> Tensor:
+    """Zero-extend the last axis to ``target_length`` samples (reference _fftconv.py:23-29)."""
+    extra = target_length - tensor.shape[-1]
+    if extra == 0:
+        return tensor
+    if extra < 0:  # F.pad semantics: a negative amount crops
+        return tensor[..., :target_length]
+    out = tensor.new_zeros(tensor.shape[:-1] + (target_length,))
+    out[..., : tensor.shape[-1]] = tensor
+    return out
+
+
+def unfold(x: Tensor, kernel_size: int, stride: int) -> Tensor:
+    """Overlapping frames of the last axis as a zero-copy view ``[*, F, kernel_size]``,
+    ``F = 1 + ceil((max(T, kernel_size) - kernel_size) / stride)``; the tail is zero-padded
+    so the last frame is complete (reference _fftconv.py:32-67).  The native overlap-save
+    kernels never materialise frames; this helper exists for callers of the reference API."""
+    length = x.shape[-1]
+    n_frames = -(-(max(length, kernel_size) - kernel_size) // stride) + 1
+    padded = pad_to(x, (n_frames - 1) * stride + kernel_size).contiguous()
+    return padded.unfold(-1, kernel_size, stride)
+
+
 def fft_conv1d(x: Tensor, kernel: Tensor, padding: tuple[int, int] = (0, 0), block_ratio: float = 5.0) -> Tensor:
     if x.ndim != 3:
         raise ValueError(f"expected [B, C, T], got {tuple(x.shape)}")

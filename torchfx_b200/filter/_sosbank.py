@@ -49,7 +49,9 @@ class SosBank:
         kb = max(r.shape[0] for r in rows)
         if kb > MAX_KB:
             return None
-        key = tuple(r.data_ptr() for r in rows) + tuple(int(r._version) for r in rows)
+        # keyed on CONTENT: a redesign (new cutoff + compute_coefficients) may hand back a tensor at the same
+        # address with the same version counter, and the rows are a few hundred bytes of host memory
+        key = tuple(r.detach().cpu().contiguous().numpy().tobytes() for r in rows)
         if key != self._sos_key:
             ident = torch.tensor([1.0, 0.0, 0.0, 1.0, 0.0, 0.0], dtype=torch.float64)
             sos = ident.repeat(len(rows), kb, 1)

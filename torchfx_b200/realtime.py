@@ -109,7 +109,13 @@ class StreamProcessor:
         g = 1.0
         for e in gains:
             g *= e.linear_gain()
-        key = (tuple(id(f) for f in filters), tuple(getattr(f, "fs", None) for f in filters), g)
+        for f in filters:
+            if f._sos is None:
+                f.compute_coefficients()
+        # content of every filter's coefficients is part of the key: a filter redesigned between calls
+        # (same object, same fs) must not keep streaming through the old fused cascade
+        key = (tuple(id(f) for f in filters), tuple(getattr(f, "fs", None) for f in filters), g,
+               tuple(f._sos.detach().cpu().contiguous().numpy().tobytes() for f in filters))
         if self._fused is None or self._fused_key != key:
             self._fused = FusedSOSCascade(*filters, gain=g)
             self._fused_key = key

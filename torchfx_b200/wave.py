@@ -50,42 +50,56 @@ class Wave:
         """Group consecutive IIR/Biquad steps; a run of >= 2 becomes ONE FusedSOSCascade
         (fresh instance => zero state per materialisation, reference wave.py:216-233).
 
-        With ``FOLD_GAIN`` (module switch, default on) a non-clamping ``Gain`` next to or
-        between IIR steps does not break the run: scaling is linear, so
-        its factor is multiplied into the b-coefficients of the fused cascade and the
-        separate 8 B/sample pass of reference wave.py:227-233 disappears.  A run that holds
-        a single IIR keeps the reference's behaviour (the module itself runs and keeps its
-        own state), so gains around it stay separate steps."""
+        With ``FOLD_GAIN`` (module switch, default on) a non-clamping ``Gain`` between two
+        such runs, or before / after one, does not cost a pass of its own (SURVEY.md 8f
+        row 3): scaling is linear, so its factor is multiplied into the b-coefficients and
+        the neighbouring fused runs become one cascade.  Folding never changes WHICH modules
+        run statefully: a lone IIR between gains is run by the reference as the module
+        itself, carrying its DF1 state from one materialisation to the next
+        (wave.py:227-233), so it stays a step of its own here as well and gains that touch
+        only such lone filters stay separate ``Gain`` steps."""
         from .effect import Gain
         from .filter.biquad import Biquad
         from .filter.fused import FusedSOSCascade
         from .filter.iir import IIR
 
         plan: list[nn.Module] = []
-        run: list[nn.Module] = []
+        part: list[nn.Module] = []  # gains and IIR runs of length >= 2 that may merge
 
-        def close_run() -> None:
-            filters = [m for m in run if isinstance(m, (IIR, Biquad))]
-            if len(filters) >= 2:
-                # gains at the tail of the run that follow the last filter still fold
+        def close_part() -> None:
+            filters = [m for m in part if isinstance(m, (IIR, Biquad))]
+            if filters:
                 g = 1.0
-                for m in run:
+                for m in part:
                     if isinstance(m, Gain):
                         g *= m.linear_gain()
                 plan.append(FusedSOSCascade(*filters, gain=g))
             else:
-                plan.extend(run)
-            run.clear()
+                plan.extend(part)
+            part.clear()
 
-        for step in self._pipeline:
+        steps = self._pipeline
+        i = 0
+        while i < len(steps):
+            step = steps[i]
             if isinstance(step, (IIR, Biquad)):
-                run.append(step)
-            elif FOLD_GAIN and isinstance(step, Gain) and not step.clamp:
-                run.append(step)
+                j = i
+                while j < len(steps) and isinstance(steps[j], (IIR, Biquad)):
+                    j += 1
+                if j - i >= 2:
+                    part.extend(steps[i:j])
+                else:  # a lone filter runs as itself (stateful) and separates what is around it
+                    close_part()
+                    plan.append(step)
+                i = j
+                continue
+            if FOLD_GAIN and isinstance(step, Gain) and not step.clamp:
+                part.append(step)
             else:
-                close_run()
+                close_part()
                 plan.append(step)
-        close_run()
+            i += 1
+        close_part()
         return plan
 
     def _materialize(self) -> None:
