@@ -1,5 +1,5 @@
-"""GPU parity of the FIR kernels (tfx_fir_f32: shared-memory direct form and partitioned
-overlap-save with in-kernel radix-4 FFTs) against the f64-accumulating oracle and the
+"""GPU parity of the FIR kernels (tfx_fir_f32: shared-memory direct form and the persistent partitioned
+overlap-save kernel with its own 16384-point shared-memory FFTs) against the f64-accumulating oracle and the
 reference-generated golden vectors.  Mirrors the reference's tests/test_fftconv.py:65-123 and
 tests/test_fir.py:14-131 (their tolerance: 1e-4; here 1e-5 of max|y| as north_star asks)."""
 from __future__ import annotations
@@ -68,10 +68,10 @@ def test_tap_counts_both_algorithms(algo, K):
 
 
 @pytest.mark.parametrize("K,T", [(2048, 5000), (2049, 5000), (5000, 3000), (4096, 4096), (12345, 40000), (300, 100),
-                                 (20000, 30000), (70000, 150000), (131072, 140000)])
+                                 (20000, 30000), (70000, 150000), (131072, 140000), (8192, 8192), (8193, 16385), (16384, 100000)])
 def test_partition_edges(K, T):
-    """K around the 2048-tap partition, K > T, T around the 2048-sample block; partition counts
-    that are not a multiple of the 32-partition chunk (10, 35) and two full chunks (64)."""
+    """K around the partition sizes (2048 first version / 8192), K > T, T around a block; partition counts that are
+    not a multiple of the 8-partition chunk (9, 16 partitions) and exactly one partition."""
     rng = np.random.default_rng(K + T)
     x = rng.standard_normal((2, T)).astype(np.float32)
     b = (rng.standard_normal(K) * np.exp(-np.arange(K) / (K / 4))).astype(np.float32)
@@ -124,16 +124,30 @@ def test_shapes_and_dtype_like_reference():
         fx.filter.FIR(b, conv_mode="nope")
 
 
-@pytest.mark.parametrize("R", [1, 2, 4])
-@pytest.mark.parametrize("K,T,C", [(3000, 20000, 3), (9000, 50001, 2), (33000, 70000, 5), (65536, 40000, 1)])
-def test_transform_sizes(R, K, T, C, monkeypatch):
-    """The overlap-save path at every transform size (N = 4096 R: a radix-R stage in front of R 4096-point
-    transforms), forced with the TFX_FIR_R developer knob; odd channel counts leave a half-empty pair, T is not
-    a multiple of the hop, K is not a multiple of the partition."""
-    monkeypatch.setenv("TFX_FIR_R", str(R))
-    rng = np.random.default_rng(K + T + R)
+@pytest.mark.parametrize("knobs", [{}, {"TFX_FIR_G": "4", "TFX_FIR_LM": "1", "TFX_FIR_LI": "2"}, {"TFX_FIR_G": "12", "TFX_FIR_LM": "5", "TFX_FIR_LI": "10"},
+                                   {"TFX_FIR_V1": "1"}])
+@pytest.mark.parametrize("K,T,C", [(3000, 20000, 3), (9000, 50001, 2), (33000, 70000, 5), (65536, 40000, 1), (100000, 300000, 19)])
+def test_queue_settings_and_first_version(knobs, K, T, C, monkeypatch):
+    """The persistent overlap-save kernel under different queue settings (open channel-pair slots G, queue lags of the
+    multiply and inverse items: the schedule changes, the result must not) and the first three-kernel implementation
+    (TFX_FIR_V1); odd channel counts leave a half-empty pair, T is not a multiple of the 8192-sample hop, K is not a
+    multiple of the partition, 19 channels need more than one group of slots."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(K + T)
     x = rng.standard_normal((C, T)).astype(np.float32)
     b = (rng.standard_normal(K) * np.exp(-np.arange(K) / (K / 5.0))).astype(np.float32)
     want = oracle.fir_causal(x, b)
     y = fir_causal(torch.from_numpy(x).to(DEV), torch.from_numpy(b), _native.TFX_FIR_OLS)
+    assert rel_to_max(y.cpu().numpy(), want) < TOL
+
+
+def test_unaligned_rows_and_views():
+    """Row starts that are not 8-byte aligned (odd leading dimension / offset view) take the scalar load / store path."""
+    rng = np.random.default_rng(3)
+    base = torch.from_numpy(rng.standard_normal((3, 50001)).astype(np.float32)).to(DEV)
+    x = base[:, 1:]  # rows start at odd element offsets
+    b = (rng.standard_normal(9000) * np.exp(-np.arange(9000) / 2000.0)).astype(np.float32)
+    y = fir_causal(x, torch.from_numpy(b), _native.TFX_FIR_OLS)
+    want = oracle.fir_causal(x.cpu().numpy(), b)
     assert rel_to_max(y.cpu().numpy(), want) < TOL

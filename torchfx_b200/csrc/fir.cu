@@ -33,6 +33,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "fir_ols16k.h"
 #include "tma.cuh"
 
 namespace tfx {
@@ -825,6 +826,13 @@ OlsLayout ols_layout(int64_t C, int64_t T, int64_t K) {
     return L;
 }
 
+// The first overlap-save implementation (4096-point transforms, three kernels per slab, spectra through HBM)
+// stays reachable with TFX_FIR_V1=1 for A/B measurements; the default is the persistent kernel of fir_ols16k.cu.
+bool use_v1() {
+    const char *e = std::getenv("TFX_FIR_V1");
+    return e != nullptr && e[0] == '1';
+}
+
 int pick_algo(int algo, int64_t K) {
     if (algo == TFX_FIR_DIRECT || algo == TFX_FIR_OLS) return algo;
     return K <= kAutoDirectTaps ? TFX_FIR_DIRECT : TFX_FIR_OLS;
@@ -838,6 +846,7 @@ extern "C" {
 size_t tfx_fir_workspace_bytes(int64_t C, int64_t T, int64_t K, int algo) {
     if (C <= 0 || T <= 0 || K <= 0) return 0;
     if (tfx::pick_algo(algo, K) == TFX_FIR_DIRECT && K <= tfx::kDirectMaxTaps) return 0;
+    if (!tfx::use_v1()) return tfx::fir_ols16k_workspace_bytes(K);
     return tfx::ols_layout(C, T, K).total;
 }
 
@@ -865,6 +874,8 @@ int tfx_fir_f32(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int
         TFX_CHECK_LAUNCH("fir_direct_kernel");
         return TFX_OK;
     }
+
+    if (!use_v1()) return launch_fir_ols16k(x, y, C, T, ldx, ldy, taps, K, workspace, workspace_bytes, stream);
 
     const OlsLayout L = ols_layout(C, T, K);
     if (workspace == nullptr || workspace_bytes < L.total) {

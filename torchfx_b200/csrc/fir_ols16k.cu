@@ -1,0 +1,852 @@
+// fir_ols16k.cu -- long-impulse-response FIR: uniformly partitioned overlap-save as ONE persistent kernel.
+//
+// Replaces FIR.forward -> fft_conv1d (reference filter/fir.py:526-579, filter/_fftconv.py:107-141: pad, unfold,
+// batched rfft, complex multiply, batched irfft, slice -- about five HBM passes of torch.fft / cuFFT).
+//
+// Algorithm.  The impulse response is cut into P = ceil(K / 8192) partitions of B = 8192 taps; a block of B output
+// samples of a channel PAIR (two real channels ride in one complex transform: the filter is real, so Re / Im of
+// the inverse are the two outputs) costs one forward and one inverse 16384-point complex FFT plus the
+// frequency-domain delay line  Y_k = sum_p H_p . X_{k-p}.  Instruction budget per output sample: ~98 for the two
+// transforms + 4 P for the delay line (P = 8 for the 65 536-tap config: 130; the 4096-point version needed 212).
+//
+// What is new against the first version (three kernels per slab, spectra and products through HBM, 39.6 B/sample):
+//  * 16384-point transforms that live in shared memory (128 KB) and run on Blackwell's PACKED fp32 pipe
+//    (FADD2 / FMUL2 / FFMA2): a thread owns the two radix-16 butterflies at neighbouring positions as one
+//    float2-per-component "pair", so every butterfly instruction does two butterflies' worth of work and no
+//    value is ever moved between the halves of a register pair.  After the first (CTA-wide) radix-16 pass the
+//    transform falls apart into 16 independent 1024-point transforms, one per WARP: passes 2-4 need only
+//    __syncwarp, warps drift apart and their shared-memory phases overlap other warps' FMA phases.
+//    Every shared-memory exchange is bank-conflict free (tools/fft16k_model.py executes this exact per-thread
+//    program in numpy, checks it against numpy.fft and counts the conflicts).
+//  * ONE persistent kernel (one 512-thread CTA per SM) pulls forward-FFT, multiply-accumulate and inverse-FFT
+//    work items from an in-order queue; items wait on per-slot completion counters (acquire / release in global
+//    memory).  The queue order keeps only G = 8 channel pairs "open" at a time, so the spectra ring
+//    (G x 39 rows x 128 KB) and the products (G x 32 rows x 128 KB) are ~72 MB that are overwritten in place and
+//    stay in the 126 MB L2: HBM sees x once and y once.
+//  * The delay line multiplies [32 blocks x 128 bin pairs] tiles staged with cp.async (double buffered); a thread
+//    owns one bin pair x 8 consecutive blocks and slides a register window over the rows: 23 LDS.128 per 256 FFMA2.
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "fir_ols16k.h"
+
+namespace tfx {
+namespace {
+
+constexpr int kN = 16384;             // complex transform size
+constexpr int kB = 8192;              // partition length = hop
+constexpr int kThreads = 512;
+constexpr int kRowPairs = 8192;       // float4 (bin pairs) per spectrum row: 128 KB
+constexpr int kJ = 32;                // output blocks per (pair, time tile)
+constexpr int kPc = 8;                // partitions per staged chunk
+constexpr int kRows = kJ + kPc - 1;   // spectra rows staged per chunk
+constexpr int kChunkPairs = 128;      // bin pairs per staged chunk (one float4 per thread of a 128-thread group)
+constexpr int kItemChunks = 4;        // chunks per multiply-accumulate work item
+constexpr int kNM = kRowPairs / (kChunkPairs * kItemChunks);  // MAC items per tile
+constexpr int kR = 8;                 // blocks per thread in the MAC
+constexpr int kHalfPairs = kChunkPairs / 2;                   // bin pairs per stage of one half of the CTA
+constexpr int kHalfBuf = (kRows + kPc) * kHalfPairs * 16;     // bytes of one staging buffer of one half
+constexpr int kSmem = 4 * kHalfBuf;   // two halves x double buffer; >= the 128 KB the transforms need
+constexpr int kIpr = kJ + kNM + kJ;   // queue items per round
+constexpr int kMaxG = 16;
+constexpr int kHeaderBytes = 1024;   // workspace header: queue head and completion counters
+constexpr int kPrefetchRounds = 3;
+constexpr size_t kTraceItems = size_t(1) << 20;  // developer trace capacity (queue items)
+static_assert(kNM * kChunkPairs * kItemChunks == kRowPairs, "MAC items must tile the row");
+static_assert(kSmem >= kN * 8, "transform does not fit");
+static_assert(kJ == 4 * kR && kThreads == 8 * kHalfPairs, "MAC thread map");
+
+// L2 cache policy.  The spectra ring and the product rows are written once, read once or twice and then overwritten in
+// place: they are tagged evict_last so that the x / y streams (evict_first) do not push them out of the 126 MB L2 before
+// they are overwritten -- an evicted dirty row costs a DRAM write AND a DRAM read for nothing.
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void st_keep16(float4 *p, float4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ float4 ld_keep16(const float4 *p, uint64_t pol) {  // L2 only (written by other SMs), keep in L2
+    float4 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float2 ld_stream8(const float *p, uint64_t pol) {  // read-only input stream: no L1 allocation, first out of L2
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+// The completion signal of an item (release fence + counter increment) is DEFERRED into the next item: issued
+// right after the item's stores, the fence waits ~2 us for 128 KB of writes to drain while the whole CTA idles
+// (measured: 4138 cycles per forward item); after the next item's first CTA barrier the writes have long landed
+// and the fence is cheap.  A pending signal is flushed before this CTA starts to spin on a dependency, so a CTA
+// never waits on a counter that its own unsent signal would complete.
+// The control thread (queue pull, dependency wait, completion signal) sits in the LAST warp: in the staggered
+// transforms that warp waits for the first half of the CTA anyway, so its fences cost nothing on the critical path.
+constexpr int kCtl = kThreads - 32;
+struct Deferred {
+    unsigned *pending;  // meaningful in the control thread only
+    __device__ __forceinline__ void flush() {
+        if (threadIdx.x == kCtl && pending != nullptr) {
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            atomicAdd(pending, 1u);
+            pending = nullptr;
+        }
+    }
+};
+// developer phase timing (trace mode only): thread 0 adds clock64() deltas to 64-bit accumulators behind the trace
+struct PhaseClock {
+    unsigned long long *acc;  // NULL: off
+    long long t;
+    __device__ __forceinline__ void start() {
+        if (acc != nullptr && threadIdx.x == 0) t = clock64();
+    }
+    __device__ __forceinline__ void lap(int slot) {
+        if (acc != nullptr && threadIdx.x == 0) {
+            const long long n = clock64();
+            atomicAdd(acc + slot, static_cast<unsigned long long>(n - t));
+            t = n;
+        }
+    }
+};
+// ------------------------------------------------------------------------------------------------------------
+// packed fp32 pairs
+// ------------------------------------------------------------------------------------------------------------
+typedef float2 p2;
+__device__ __forceinline__ p2 neg2(p2 a) { return make_float2(-a.x, -a.y); }  // folds into operand modifiers
+__device__ __forceinline__ p2 add2(p2 a, p2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ p2 sub2(p2 a, p2 b) { return __fadd2_rn(a, neg2(b)); }
+__device__ __forceinline__ p2 mul2(p2 a, p2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ p2 fma2(p2 a, p2 b, p2 c) { return __ffma2_rn(a, b, c); }
+struct c2 {  // two complex numbers: (re.x, im.x) and (re.y, im.y)
+    p2 re, im;
+};
+__device__ __forceinline__ c2 cadd(c2 a, c2 b) { return c2{add2(a.re, b.re), add2(a.im, b.im)}; }
+__device__ __forceinline__ c2 csub(c2 a, c2 b) { return c2{sub2(a.re, b.re), sub2(a.im, b.im)}; }
+__device__ __forceinline__ c2 cmul(c2 x, c2 w) {
+    return c2{fma2(x.re, w.re, neg2(mul2(x.im, w.im))), fma2(x.re, w.im, mul2(x.im, w.re))};
+}
+__device__ __forceinline__ c2 cmulc(c2 x, c2 w) {  // x * conj(w)
+    return c2{fma2(x.re, w.re, mul2(x.im, w.im)), fma2(x.im, w.re, neg2(mul2(x.re, w.im)))};
+}
+// t * W_16^k, W_16 = exp(-2 pi i / 16); k is a compile-time constant once the callers are unrolled
+__device__ __forceinline__ c2 rot16(c2 t, int k) {
+    constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
+    float c, s;  // W = c + i s
+    switch (k & 15) {
+        case 0: return t;
+        case 4: return c2{t.im, neg2(t.re)};
+        case 1: c = c1, s = -s1; break;
+        case 2: c = h, s = -h; break;
+        case 3: c = s1, s = -c1; break;
+        case 6: c = -h, s = -h; break;
+        case 9: c = -c1, s = s1; break;
+        default: c = 1.f, s = 0.f; break;  // not reached (k = m * r with m, r in 1..3)
+    }
+    const p2 cc = make_float2(c, c), ss = make_float2(s, s);
+    return c2{fma2(t.re, cc, neg2(mul2(t.im, ss))), fma2(t.re, ss, mul2(t.im, cc))};
+}
+
+// radix-4 butterflies on pairs: forward = decimation in frequency (twiddles on outputs 1..3),
+// inverse = decimation in time with conjugate twiddles on inputs 1..3
+__device__ __forceinline__ void bfly4_dif(c2 &a, c2 &b, c2 &c, c2 &d, c2 w1, c2 w2, c2 w3) {
+    const c2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d);
+    const c2 t3 = c2{sub2(b.im, d.im), sub2(d.re, b.re)};  // (b - d) * (-i)
+    a = cadd(t0, t2);
+    b = cmul(cadd(t1, t3), w1);
+    c = cmul(csub(t0, t2), w2);
+    d = cmul(csub(t1, t3), w3);
+}
+__device__ __forceinline__ void bfly4_dit_inv(c2 &a, c2 &b, c2 &c, c2 &d, c2 w1, c2 w2, c2 w3) {
+    b = cmulc(b, w1);
+    c = cmulc(c, w2);
+    d = cmulc(d, w3);
+    const c2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, d);
+    const c2 t3 = c2{sub2(d.im, b.im), sub2(b.re, d.re)};  // (b - d) * (+i)
+    a = cadd(t0, t2);
+    b = cadd(t1, t3);
+    c = csub(t0, t2);
+    d = csub(t1, t3);
+}
+
+// Twiddles of one thread for one radix-16 pass at position j of a 16q-point group, W = exp(-2 pi i / N):
+//   a_r = W_{16q}^{r j},  w_r = W_{4q}^{r j},  r = 1..3.
+// The stage-A twiddle of the butterfly over slots {m, m+4, m+8, m+12} is W_{16q}^{(j + m q) r} = a_r * W_16^{m r}.
+struct Tw6 {
+    c2 a1, a2, a3, w1, w2, w3;
+};
+// Table: float4 (re.x, re.y, im.x, im.y) per twiddle, laid out [6][entries] so that lanes load consecutive float4.
+constexpr int kTw1 = 0;               // pass 1: entry = tid (512)
+constexpr int kTw2 = 6 * 512;         // pass 2: entry = lane (32)
+constexpr int kTw3 = kTw2 + 6 * 32;   // pass 3: entry = jh (2)
+constexpr int kTwTotal = kTw3 + 6 * 2;
+__device__ __forceinline__ c2 ld_tw(const float4 *p) {
+    const float4 u = __ldg(p);
+    return c2{make_float2(u.x, u.y), make_float2(u.z, u.w)};
+}
+__device__ __forceinline__ Tw6 load_tw(const float4 *__restrict__ tab, int entry, int stride) {
+    Tw6 t;
+    t.a1 = ld_tw(tab + entry);
+    t.a2 = ld_tw(tab + stride + entry);
+    t.a3 = ld_tw(tab + 2 * stride + entry);
+    t.w1 = ld_tw(tab + 3 * stride + entry);
+    t.w2 = ld_tw(tab + 4 * stride + entry);
+    t.w3 = ld_tw(tab + 5 * stride + entry);
+    return t;
+}
+
+// Register slot 4 r + r2 of a radix-16 result holds output digit r + 4 r2.
+__device__ __forceinline__ constexpr int slot_digit(int s) { return (s >> 2) + 4 * (s & 3); }
+
+__device__ __forceinline__ void radix16_dif(c2 (&v)[16], const Tw6 &t) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+        bfly4_dif(v[m], v[m + 4], v[m + 8], v[m + 12], rot16(t.a1, m), rot16(t.a2, 2 * m), rot16(t.a3, 3 * m));
+#pragma unroll
+    for (int a = 0; a < 4; ++a) bfly4_dif(v[4 * a], v[4 * a + 1], v[4 * a + 2], v[4 * a + 3], t.w1, t.w2, t.w3);
+}
+__device__ __forceinline__ void radix16_dit_inv(c2 (&v)[16], const Tw6 &t) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) bfly4_dit_inv(v[4 * a], v[4 * a + 1], v[4 * a + 2], v[4 * a + 3], t.w1, t.w2, t.w3);
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+        bfly4_dit_inv(v[m], v[m + 4], v[m + 8], v[m + 12], rot16(t.a1, m), rot16(t.a2, 2 * m), rot16(t.a3, 3 * m));
+}
+
+// Pair slot of element (k2, u5) inside a warp's 512-slot region for the pass 2 -> 3 and 3 -> 4 exchanges:
+// the low four bits are XOR-ed with k2 so that both the writers (lanes = u5) and the readers (lanes = k2) of a
+// 64-bit access touch 16 different bank pairs per half-warp.
+__device__ __forceinline__ int xslot(int k2, int u5) { return k2 * 32 + ((u5 & 16) | ((u5 ^ k2) & 15)); }
+
+// Named barrier 1 staggers the two halves of the CTA: warps 8..15 start a transform's warp-local passes only after
+// warps 0..7 have issued their first shared-memory phase, so that from then on one half's shared-memory traffic
+// runs under the other half's butterflies (in lock step the two pipes simply alternate: measured 7.8 us per
+// transform against 3.3 us of FMA-pipe time).
+__device__ __forceinline__ void half_arrive() { asm volatile("bar.arrive 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void half_wait() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------------------
+// The 16384-point transform.  n = n1 * 1024 + d2 * 64 + d3 * 4 + jh * 2 + jl  (see tools/fft16k_model.py):
+//   pass 1  radix-16 over n1, CTA-wide: thread t owns positions r = 2 t, 2 t + 1            -> sub-transform k1 = warp
+//   pass 2  radix-16 over d2, warp:     lane l owns pair slot sp = l
+//   pass 3  radix-16 over d3, warp:     lane l = (jh = l >> 4, k2 = l & 15)
+//   pass 4  radix-2 over jh on pairs, radix-2 over jl ACROSS the halves of a pair (scalar adds)
+// Output bin k1 + 16 (k2 + 16 (k3 + 16 (r + 2 r2))) is half r2 of the float4 (re0, re1, im0, im1) at pair index
+// (i * 2 + r) * 512 + tid, k3 = 8 (lane >> 4) + i.  Spectra are only ever multiplied point-wise with spectra in
+// the same order, so the order is never undone.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ p2 *warp_re(unsigned char *smem, int warp) { return reinterpret_cast<p2 *>(smem) + warp * 1024; }
+
+// v[m] on entry: pair (n = 1024 m + 2 tid, + 1), re = channel a, im = channel b.  `scale` multiplies the result.
+__device__ __forceinline__ void fft16k_fwd(c2 (&v)[16], unsigned char *smem, const float4 *__restrict__ tw,
+                                           float4 *__restrict__ row_out, float scale, PhaseClock &pc, Deferred &df) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    radix16_dif(v, load_tw(tw + kTw1, tid, 512));
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        p2 *R = warp_re(smem, slot_digit(s));
+        R[tid] = v[s].re;
+        R[512 + tid] = v[s].im;
+    }
+    __syncthreads();
+    pc.lap(3);
+    p2 *R = warp_re(smem, warp);
+    p2 *I = R + 512;
+    if (warp >= 8) {
+        df.flush();
+        half_wait();
+    }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = c2{R[m * 32 + lane], I[m * 32 + lane]};
+    if (warp < 8) half_arrive();
+    radix16_dif(v, load_tw(tw + kTw2, lane, 32));
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const int o = xslot(slot_digit(s), lane);
+        R[o] = v[s].re;
+        I[o] = v[s].im;
+    }
+    __syncwarp();
+    const int hi = lane >> 4, k2 = lane & 15;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const int o = xslot(k2, 2 * m + hi);
+        v[m] = c2{R[o], I[o]};
+    }
+    radix16_dif(v, load_tw(tw + kTw3, hi, 2));
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const int o = xslot(k2, 2 * slot_digit(s) + hi);
+        R[o] = v[s].re;
+        I[o] = v[s].im;
+    }
+    __syncwarp();
+    pc.lap(4);
+    const uint64_t pol = policy_evict_last();
+    const p2 sc = make_float2(scale, scale);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int k3 = 8 * hi + i;
+        const int o0 = xslot(k2, 2 * k3), o1 = xslot(k2, 2 * k3 + 1);
+        const c2 v0 = c2{R[o0], I[o0]}, v1 = c2{R[o1], I[o1]};
+        c2 s = cadd(v0, v1), d = csub(v0, v1);
+        s.re = mul2(s.re, sc);
+        s.im = mul2(s.im, sc);
+        d.re = mul2(d.re, sc);
+        d.im = mul2(d.im, sc);
+        // r = 0: A + B, A - B;  r = 1: A + (-i) B, A - (-i) B   (A = half x, B = half y of the pair)
+        st_keep16(row_out + (i * 2 + 0) * 512 + tid, make_float4(s.re.x + s.re.y, s.re.x - s.re.y, s.im.x + s.im.y, s.im.x - s.im.y), pol);
+        st_keep16(row_out + (i * 2 + 1) * 512 + tid, make_float4(d.re.x + d.im.y, d.re.x - d.im.y, d.im.x - d.re.y, d.im.x + d.re.y), pol);
+    }
+    pc.lap(5);
+}
+
+// Inverse (unscaled, the 1/N lives in H): row_in in the forward's output order; on return v[m] = pair of time
+// samples (n = 1024 m + 2 tid, + 1).
+__device__ __forceinline__ void fft16k_inv(c2 (&v)[16], unsigned char *smem, const float4 *__restrict__ tw,
+                                           const float4 *__restrict__ row_in, PhaseClock &pc, Deferred &df) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    p2 *R = warp_re(smem, warp);
+    p2 *I = R + 512;
+    const int hi = lane >> 4, k2 = lane & 15;
+    float4 in[16];
+    const uint64_t pol = policy_evict_last();
+#pragma unroll
+    for (int e = 0; e < 16; ++e) in[e] = ld_keep16(row_in + e * 512 + tid, pol);  // written by other SMs: L2, not L1
+    if (warp >= 8) {
+        df.flush();
+        half_wait();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 a = in[2 * i], b = in[2 * i + 1];  // (re0, re1, im0, im1) for r = 0 and r = 1
+        // r = 0: A = o0 + o1, B = o0 - o1;  r = 1: A = o0 + o1, B = i (o0 - o1)
+        const c2 p0 = c2{make_float2(a.x + a.y, a.x - a.y), make_float2(a.z + a.w, a.z - a.w)};
+        const c2 p1 = c2{make_float2(b.x + b.y, b.w - b.z), make_float2(b.z + b.w, b.x - b.y)};
+        const c2 v0 = cadd(p0, p1), v1 = csub(p0, p1);
+        const int k3 = 8 * hi + i;
+        const int o0 = xslot(k2, 2 * k3), o1 = xslot(k2, 2 * k3 + 1);
+        R[o0] = v0.re;
+        I[o0] = v0.im;
+        R[o1] = v1.re;
+        I[o1] = v1.im;
+    }
+    if (warp < 8) half_arrive();
+    __syncwarp();
+    pc.lap(6);
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const int o = xslot(k2, 2 * slot_digit(s) + hi);
+        v[s] = c2{R[o], I[o]};
+    }
+    radix16_dit_inv(v, load_tw(tw + kTw3, hi, 2));
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const int o = xslot(k2, 2 * m + hi);
+        R[o] = v[m].re;
+        I[o] = v[m].im;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const int o = xslot(slot_digit(s), lane);
+        v[s] = c2{R[o], I[o]};
+    }
+    radix16_dit_inv(v, load_tw(tw + kTw2, lane, 32));
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        R[m * 32 + lane] = v[m].re;
+        I[m * 32 + lane] = v[m].im;
+    }
+    pc.lap(7);
+    __syncthreads();
+    pc.lap(8);
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const p2 *Rk = warp_re(smem, slot_digit(s));
+        v[s] = c2{Rk[tid], Rk[512 + tid]};
+    }
+    radix16_dit_inv(v, load_tw(tw + kTw1, tid, 512));
+}
+
+__global__ void fir16k_twiddle_kernel(float4 *tab) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= kTwTotal) return;
+    int i, ja, unit;  // twiddle i (0..5) of the entry whose halves sit at positions ja and ja + 1; exponent unit N / (16 q)
+    if (e < kTw2) {
+        i = e / 512;
+        ja = 2 * (e % 512);
+        unit = 1;
+    } else if (e < kTw3) {
+        i = (e - kTw2) / 32;
+        ja = 2 * ((e - kTw2) % 32);
+        unit = 16;
+    } else {
+        i = (e - kTw3) / 2;
+        ja = 2 * ((e - kTw3) % 2);
+        unit = 256;
+    }
+    const int r = (i % 3) + 1;
+    const int mult = unit * (i < 3 ? 1 : 4) * r;  // a_r = W_N^{unit r j}, w_r = W_N^{4 unit r j}
+    double s0, c0, s1, c1;
+    sincospi(-2.0 * static_cast<double>((static_cast<int64_t>(mult) * ja) % kN) / kN, &s0, &c0);
+    sincospi(-2.0 * static_cast<double>((static_cast<int64_t>(mult) * (ja + 1)) % kN) / kN, &s1, &c1);
+    tab[e] = make_float4(static_cast<float>(c0), static_cast<float>(c1), static_cast<float>(s0), static_cast<float>(s1));
+}
+
+// H[p] = FFT(taps[p B : (p + 1) B] zero-padded to N) / N, one CTA per partition
+__global__ void __launch_bounds__(kThreads, 1) fir16k_taps_kernel(const float *__restrict__ taps, int64_t K, float4 *__restrict__ H,
+                                                                 const float4 *__restrict__ tw) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int64_t p = blockIdx.x;
+    c2 v[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const int n = 1024 * m + 2 * threadIdx.x;
+        const int64_t j = p * kB + n;
+        const float a = (n < kB && j < K) ? __ldg(&taps[j]) : 0.f;
+        const float b = (n + 1 < kB && j + 1 < K) ? __ldg(&taps[j + 1]) : 0.f;
+        v[m] = c2{make_float2(a, b), make_float2(0.f, 0.f)};
+    }
+    PhaseClock pc{nullptr, 0};
+    Deferred df{nullptr};
+    fft16k_fwd(v, smem, tw, H + p * kRowPairs, 1.0f / kN, pc, df);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// The persistent kernel
+// ------------------------------------------------------------------------------------------------------------
+struct Params {
+    const float *x;
+    float *y;
+    int64_t C, T, ldx, ldy;
+    int P, npairs, nblk;
+    int NJ;        // time tiles per pair
+    int NU;        // tiles per slot = pair groups * NJ
+    int G, LM, LI;  // open slots, queue lag of the MAC items / of the inverse items (rounds)
+    int RR;        // ring rows per slot = kJ + P - 1
+    int npc;       // partition chunks = ceil(P / kPc)
+    int nitems;
+    int vec_ok;    // rows 8-byte aligned: 64-bit global accesses allowed
+    float4 *Z;     // [G][RR][kRowPairs]
+    float4 *Y;     // [G][kJ][kRowPairs]
+    const float4 *H;  // [P][kRowPairs]
+    const float4 *tw;
+    uint4 *trace;   // developer trace (TFX_FIR_TRACE=1): per queue item {type << 24 | sub, wait ns, run ns, start ns}, else NULL
+    unsigned *ctr;  // [0] queue head; [16 + i] forward items done, [32 + i] MAC items done, [48 + i] inverse items done
+};
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void wait_count(const unsigned *ctr, unsigned need, Deferred &df) {
+    if (need == 0) return;  // CTA-uniform
+    if (threadIdx.x == kCtl && ld_acquire(ctr) < need) {
+        df.flush();
+        // Every dependency sits earlier in the in-order queue, so this wait always ends; the bound turns a
+        // scheduling bug into a launch error instead of a hung GPU.
+        unsigned spins = 0;
+        while (ld_acquire(ctr) < need) {
+            __nanosleep(64);
+            if (++spins > (1u << 27)) __trap();
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void forward_item(const Params &p, unsigned char *smem, int pair, int k, float4 *row, PhaseClock &pc, Deferred &df) {
+    const int tid = threadIdx.x;
+    const int64_t ca = 2 * static_cast<int64_t>(pair), cb = ca + 1;
+    const bool has_b = cb < p.C;
+    const float *xa = p.x + ca * p.ldx;
+    const float *xb = p.x + (has_b ? cb : ca) * p.ldx;
+    const int64_t nbase = (static_cast<int64_t>(k) - 1) * kB + 2 * tid;
+    c2 v[16];
+    const uint64_t polx = policy_evict_first();
+    if (k >= 1 && p.vec_ok && (static_cast<int64_t>(k) + 1) * kB <= p.T) {  // whole block inside the signal
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const float2 a = ld_stream8(xa + nbase + 1024 * m, polx);
+            const float2 b = ld_stream8(xb + nbase + 1024 * m, polx);
+            v[m] = c2{a, b};
+        }
+    } else {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int64_t n = nbase + 1024 * m;
+            const bool ok0 = n >= 0 && n < p.T, ok1 = n + 1 >= 0 && n + 1 < p.T;
+            v[m] = c2{make_float2(ok0 ? __ldg(xa + n) : 0.f, ok1 ? __ldg(xa + n + 1) : 0.f),
+                      make_float2(ok0 ? __ldg(xb + n) : 0.f, ok1 ? __ldg(xb + n + 1) : 0.f)};
+        }
+    }
+    if (!has_b) {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m].im = make_float2(0.f, 0.f);
+    }
+    fft16k_fwd(v, smem, p.tw, row, 1.0f, pc, df);
+}
+
+__device__ __forceinline__ void inverse_item(const Params &p, unsigned char *smem, int pair, int k, const float4 *row, PhaseClock &pc, Deferred &df) {
+    const int tid = threadIdx.x;
+    c2 v[16];
+    fft16k_inv(v, smem, p.tw, row, pc, df);
+    const int64_t ca = 2 * static_cast<int64_t>(pair), cb = ca + 1;
+    const bool has_b = cb < p.C;
+    float *ya = p.y + ca * p.ldy;
+    float *yb = p.y + cb * p.ldy;
+    const int64_t nbase = static_cast<int64_t>(k) * kB + 2 * tid;
+    const bool whole = p.vec_ok && (static_cast<int64_t>(k) + 1) * kB <= p.T;
+#pragma unroll
+    for (int m = 8; m < 16; ++m) {  // the valid half of the block
+        const int64_t n = nbase + 1024 * (m - 8);
+        if (whole) {
+            asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(ya + n), "f"(v[m].re.x), "f"(v[m].re.y) : "memory");
+            if (has_b) asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(yb + n), "f"(v[m].im.x), "f"(v[m].im.y) : "memory");
+        } else {
+            if (n < p.T) {
+                ya[n] = v[m].re.x;
+                if (has_b) yb[n] = v[m].im.x;
+            }
+            if (n + 1 < p.T) {
+                ya[n + 1] = v[m].re.y;
+                if (has_b) yb[n + 1] = v[m].im.y;
+            }
+        }
+    }
+    pc.lap(9);
+}
+
+// Y[slot][jj][pairs of this item] = sum_p H[p] . X[block jt*J + jj - p]
+//
+// A stage = [39 spectra rows + 8 taps rows] x 128 bin pairs (2 KB per row), double buffered.  Staging is 12
+// zero-filling 16-byte cp.async per thread whose ring slot, source and destination advance by constants (the first
+// version redid a modulo and three 64-bit multiplies per copy -- twice the issue slots of the multiply itself --
+// and needed two CTA barriers per stage: 4.6 us per stage against 1.1 us of FMA time; one bulk copy per row,
+// 47 per stage from one warp, measured 3.1 us per stage: the per-SM bulk-copy request rate).  One barrier per
+// stage: the copy of stage e + 1 is issued right after it and runs under the multiply of stage e.
+// Thread map of the multiply: a warp owns 8 consecutive bin pairs x all 32 blocks, lane = (pair, block group of
+// 8), so that the four block groups of a warp read the SAME taps (one 128-byte wavefront instead of four).
+__device__ __forceinline__ void cp16_zfill(void *smem_dst, const void *gmem_src, bool valid, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+                 "r"(valid ? 16 : 0), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void mac_item(const Params &p, unsigned char *smem, int slot, int u, int jt, int item, PhaseClock &pk, Deferred &df) {
+    // The two halves of the CTA (8 warps each) run INDEPENDENT double-buffered pipelines over alternate 64-pair half
+    // chunks, synchronised by their own named barrier: one half's copy / wait phase runs under the other half's
+    // multiply (with one CTA-wide pipeline all warps copy, wait and multiply in lock step: 6700 cycles per stage for
+    // 2048 cycles of FMA).
+    const int tid = threadIdx.x, half = tid >> 8, th = tid & 255, lane = tid & 31, wh = th >> 5;
+    const int fl = wh * 8 + (lane & 7);  // bin pair inside the half chunk
+    const int kg = lane >> 3;            // blocks [8 kg, 8 kg + 8)
+    const int rq = th >> 6, piece = th & (kHalfPairs - 1);  // staging: rows rq, rq + 4, ..., 16-byte piece of the row
+    const int nstages = kItemChunks * p.npc;  // per half: kItemChunks half chunks
+    const float4 *Zs_g = p.Z + static_cast<int64_t>(slot) * p.RR * kRowPairs;
+    const uint64_t pol = policy_evict_last();
+    unsigned char *hbuf = smem + half * (2 * kHalfBuf);
+    const int bar_id = 2 + half;
+
+    auto issue = [&](int e, int b) {
+        const int c = e / p.npc, pc = e - c * p.npc;
+        const int col = (item * kItemChunks * 2 + 2 * c + half) * kHalfPairs + piece;
+        unsigned char *dst = hbuf + b * kHalfBuf + (rq * kHalfPairs + piece) * 16;
+        // local row lr <-> block jt*J - 8 pc - 7 + lr, ring row id u*J - 8 pc - 7 + lr; rows kRows.. are the taps.
+        // Rows that only partitions >= P would read are zero-filled as well: their ring slots alias rows that may
+        // never have been written (0 x NaN).
+        const int plmax = min(kPc - 1, p.P - 1 - kPc * pc);
+        const int rel0 = rq - (kPc - 1) - kPc * pc;
+        int blk = jt * kJ + rel0;
+        int rid = (u * kJ + rel0) % p.RR;
+        if (rid < 0) rid += p.RR;
+        const float4 *src = Zs_g + static_cast<int64_t>(rid) * kRowPairs + col;
+        const int64_t wrap = static_cast<int64_t>(p.RR) * kRowPairs;
+#pragma unroll
+        for (int i = 0; i < (kRows + kPc + 3) / 4; ++i) {
+            const int lr = rq + 4 * i;
+            if (lr < kRows) {
+                const bool ok = blk >= 0 && blk < p.nblk && lr >= (kPc - 1) - plmax;
+                cp16_zfill(dst, ok ? src : Zs_g, ok, pol);
+                blk += 4;
+                rid += 4;
+                src += 4 * kRowPairs;
+                if (rid >= p.RR) {
+                    rid -= p.RR;
+                    src -= wrap;
+                }
+            } else if (lr < kRows + kPc) {
+                const int pp = kPc * pc + (lr - kRows);
+                const bool ok = pp < p.P;
+                cp16_zfill(dst, p.H + static_cast<int64_t>(ok ? pp : 0) * kRowPairs + col, ok, pol);
+            }
+            dst += 4 * kHalfPairs * 16;
+        }
+        cp_async_commit();
+    };
+
+    c2 acc[kR];
+    issue(0, 0);
+    for (int e = 0; e < nstages; ++e) {
+        const int b = e & 1;
+        cp_async_wait<0>();
+        asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");  // stage e has landed for this half; it is done reading the other buffer
+        if (e == 0) df.flush();
+        pk.lap(0);
+        if (e + 1 < nstages) issue(e + 1, b ^ 1);
+        pk.lap(1);
+        const int c = e / p.npc, pc = e - c * p.npc;
+        if (pc == 0) {
+#pragma unroll
+            for (int r = 0; r < kR; ++r) acc[r] = c2{make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        }
+        {
+            const float4 *Zs = reinterpret_cast<const float4 *>(hbuf + b * kHalfBuf) + fl;
+            const float4 *Hs = Zs + kRows * kHalfPairs;
+            const int m0 = kg * kR + (kPc - 1);  // local row of (block jj = 0, partition pl = 0) for this thread
+            c2 w[kR];  // w[(jj - pl) & 7] = row m0 + jj - pl
+#pragma unroll
+            for (int m = 0; m < kR; ++m) {
+                const float4 z = Zs[(m0 + m) * kHalfPairs];
+                w[m] = c2{make_float2(z.x, z.y), make_float2(z.z, z.w)};
+            }
+#pragma unroll
+            for (int pl = 0; pl < kPc; ++pl) {  // (skipping the partitions a short impulse response does not have costs
+                                                //  more in spills than it saves: every chunk multiplies all 8, zeros included)
+                const float4 hh = Hs[pl * kHalfPairs];
+                const p2 hr = make_float2(hh.x, hh.y), hi = make_float2(hh.z, hh.w), nhi = neg2(hi);
+#pragma unroll
+                for (int jj = 0; jj < kR; ++jj) {
+                    const c2 z = w[(jj - pl) & (kR - 1)];
+                    acc[jj].re = fma2(hr, z.re, acc[jj].re);
+                    acc[jj].re = fma2(nhi, z.im, acc[jj].re);
+                    acc[jj].im = fma2(hr, z.im, acc[jj].im);
+                    acc[jj].im = fma2(hi, z.re, acc[jj].im);
+                }
+                if (pl + 1 < kPc) {
+                    const float4 z = Zs[(m0 - pl - 1) * kHalfPairs];
+                    w[(kR - 1 - pl) & (kR - 1)] = c2{make_float2(z.x, z.y), make_float2(z.z, z.w)};
+                }
+            }
+        }
+        if (pc == p.npc - 1) {
+            float4 *Yp = p.Y + (static_cast<int64_t>(slot) * kJ + kg * kR) * kRowPairs + (item * kItemChunks * 2 + 2 * c + half) * kHalfPairs + fl;
+#pragma unroll
+            for (int jj = 0; jj < kR; ++jj) {
+                if (jt * kJ + kg * kR + jj < p.nblk)
+                    st_keep16(Yp + static_cast<int64_t>(jj) * kRowPairs, make_float4(acc[jj].re.x, acc[jj].re.y, acc[jj].im.x, acc[jj].im.y), pol);
+            }
+        }
+        pk.lap(2);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) fir16k_kernel(const __grid_constant__ Params p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ unsigned s_q[2];
+    if (threadIdx.x == kCtl) s_q[0] = atomicAdd(p.ctr, 1u);
+    Deferred df{nullptr};
+    for (int it = 0;; ++it) {
+        __syncthreads();  // the previous item is done with shared memory and has issued its stores; s_q[it & 1] is visible
+        const int q = static_cast<int>(s_q[it & 1]);
+        if (q >= p.nitems) break;
+        // claim the NEXT item now: a forward item's input is prefetched into L2 while this item runs
+        if (threadIdx.x == kCtl) s_q[(it + 1) & 1] = atomicAdd(p.ctr, 1u);
+        const int rho = q / kIpr, s = q - rho * kIpr;
+        int type, tile, sub;  // a round: the MAC items of tile rho - LM first (they run longest), then forward, then inverse
+        if (s < kNM) {
+            type = 1, tile = rho - p.LM, sub = s;
+        } else if (s < kNM + kJ) {
+            type = 0, tile = rho, sub = s - kNM;
+        } else {
+            type = 2, tile = rho - p.LI, sub = s - kNM - kJ;
+        }
+        if (tile < 0 || tile >= p.NU * p.G) continue;
+        if (type == 0 && rho + kPrefetchRounds < p.NU * p.G) {
+            // L2 prefetch for the forward item kPrefetchRounds rounds ahead with the same block offset: the NEW half
+            // of its input block, 2 channels x 32 KB = one 128-byte line per thread (the old half is the new
+            // half of the block before it).  Every forward item is prefetched exactly once, ~2 us ahead.
+            const int tn = rho + kPrefetchRounds;
+            const int un = tn / p.G, sl = tn - un * p.G;
+            const int gn = un / p.NJ, jn = un - gn * p.NJ;
+            const int64_t pr = static_cast<int64_t>(gn) * p.G + sl;
+            const int64_t kn = static_cast<int64_t>(jn) * kJ + sub;
+            const int64_t ch = 2 * pr + (threadIdx.x >> 8);
+            const int64_t n = kn * kB + (threadIdx.x & 255) * 32;
+            if (pr < p.npairs && kn < p.nblk && ch < p.C && n + 32 <= p.T)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + ch * p.ldx + n));
+        }
+        const int u = tile / p.G, slot = tile - u * p.G;
+        const int g = u / p.NJ, jt = u - g * p.NJ;
+        const int pair = g * p.G + slot;
+        const bool pair_ok = pair < p.npairs;
+        unsigned *fdone = p.ctr + 16 + slot, *mdone = p.ctr + 32 + slot, *idone = p.ctr + 48 + slot;
+        unsigned long long t0 = 0, t1 = 0;
+        if (p.trace != nullptr && threadIdx.x == 0) t0 = global_ns();
+        PhaseClock pk{p.trace != nullptr ? reinterpret_cast<unsigned long long *>(p.trace + kTraceItems) : nullptr, 0};
+#define TFX_TRACE_START() do { if (p.trace != nullptr && threadIdx.x == 0) t1 = global_ns(); pk.start(); } while (0)
+        if (type == 0) {
+            // ring row (u J + sub) overwrites row (u J + sub - RR), last read by the MAC items of tile u - 1
+            wait_count(mdone, static_cast<unsigned>(u) * kNM, df);
+            TFX_TRACE_START();
+            const int k = jt * kJ + sub;
+            if (pair_ok && k < p.nblk) {
+                const int rid = (u * kJ + sub) % p.RR;
+                forward_item(p, smem, pair, k, p.Z + (static_cast<int64_t>(slot) * p.RR + rid) * kRowPairs, pk, df);
+            }
+            df.flush();  // (only still pending when the item was skipped)
+            if (threadIdx.x == kCtl) df.pending = fdone;
+            pk.lap(10);
+        } else if (type == 1) {
+            wait_count(fdone, static_cast<unsigned>(u + 1) * kJ, df);  // this tile's (and every earlier tile's) spectra exist
+            wait_count(idone, static_cast<unsigned>(u) * kJ, df);      // the previous tile's products have been consumed
+            TFX_TRACE_START();
+            if (pair_ok && jt * kJ < p.nblk) mac_item(p, smem, slot, u, jt, sub, pk, df);
+            df.flush();
+            if (threadIdx.x == kCtl) df.pending = mdone;
+            pk.lap(11);
+        } else {
+            wait_count(mdone, static_cast<unsigned>(u + 1) * kNM, df);
+            TFX_TRACE_START();
+            const int k = jt * kJ + sub;
+            if (pair_ok && k < p.nblk) inverse_item(p, smem, pair, k, p.Y + (static_cast<int64_t>(slot) * kJ + sub) * kRowPairs, pk, df);
+            df.flush();
+            if (threadIdx.x == kCtl) df.pending = idone;
+            pk.lap(12);
+        }
+#undef TFX_TRACE_START
+        if (p.trace != nullptr && threadIdx.x == 0) {
+            const unsigned long long t2 = global_ns();
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            p.trace[q] = make_uint4((static_cast<unsigned>(type) << 24) | (smid << 8) | static_cast<unsigned>(sub), static_cast<unsigned>(t1 - t0),
+                                    static_cast<unsigned>(t2 - t1), static_cast<unsigned>(t0));
+        }
+    }
+    df.flush();
+}
+
+struct Layout {
+    int P, G, RR;
+    size_t off_tw, off_H, off_Z, off_Y, off_trace, total;
+};
+bool trace_on() {
+    const char *e = std::getenv("TFX_FIR_TRACE");
+    return e != nullptr && e[0] == '1';
+}
+Layout layout16k(int64_t K) {
+    Layout L{};
+    L.P = static_cast<int>((K + kB - 1) / kB);
+    L.G = 8;
+    if (const char *e = std::getenv("TFX_FIR_G")) {
+        const int g = std::atoi(e);
+        if (g >= 4 && g <= kMaxG) L.G = g;
+    }
+    L.RR = kJ + L.P - 1;
+    auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
+    const size_t row = static_cast<size_t>(kRowPairs) * sizeof(float4);
+    L.off_tw = kHeaderBytes;  // counters and the zero row first
+    L.off_H = align(L.off_tw + sizeof(float4) * kTwTotal);
+    L.off_Z = align(L.off_H + row * L.P);
+    L.off_Y = align(L.off_Z + row * L.G * L.RR);
+    L.off_trace = align(L.off_Y + row * L.G * kJ);
+    L.total = trace_on() ? align(L.off_trace + kTraceItems * sizeof(uint4) + 256) : L.off_trace;
+    return L;
+}
+
+}  // namespace
+
+size_t fir_ols16k_workspace_bytes(int64_t K) { return layout16k(K).total; }
+
+int launch_fir_ols16k(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, const float *taps, int64_t K,
+                      void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+    const Layout L = layout16k(K);
+    if (workspace == nullptr || workspace_bytes < L.total) {
+        set_error("fir: workspace of %zu bytes needed, %zu given (query tfx_fir_workspace_bytes)", L.total, workspace_bytes);
+        return TFX_EWORKSPACE;
+    }
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    Params p{};
+    p.x = x;
+    p.y = y;
+    p.C = C;
+    p.T = T;
+    p.ldx = ldx;
+    p.ldy = ldy;
+    p.P = L.P;
+    p.npairs = static_cast<int>((C + 1) / 2);
+    const int64_t nblk = (T + kB - 1) / kB;
+    TFX_REQUIRE(nblk < (int64_t(1) << 24) && C < (int64_t(1) << 24), "fir: signal too long / too many channels for the overlap-save kernel");
+    p.nblk = static_cast<int>(nblk);
+    p.NJ = (p.nblk + kJ - 1) / kJ;
+    p.G = L.G;
+    const int64_t groups = (p.npairs + p.G - 1) / p.G;
+    const int64_t NU = groups * p.NJ;
+    p.LM = 4;
+    p.LI = 8;
+    if (const char *e = std::getenv("TFX_FIR_LM")) p.LM = std::atoi(e);
+    if (const char *e = std::getenv("TFX_FIR_LI")) p.LI = std::atoi(e);
+    // every dependency must sit strictly earlier in the queue: 1 <= LM < LI < G + LM and LM < G
+    TFX_REQUIRE(p.LM >= 1 && p.LM < p.LI && p.LI < p.G + p.LM && p.LM < p.G, "fir: bad queue lags LM=%d LI=%d G=%d", p.LM, p.LI, p.G);
+    p.RR = L.RR;
+    p.npc = (p.P + kPc - 1) / kPc;
+    const int64_t nitems = (NU * p.G + p.LI) * kIpr;
+    TFX_REQUIRE(nitems < (int64_t(1) << 31) && NU * kJ < (int64_t(1) << 31), "fir: too many work items for one launch");
+    p.NU = static_cast<int>(NU);
+    p.nitems = static_cast<int>(nitems);
+    p.vec_ok = (reinterpret_cast<uintptr_t>(x) % 8 == 0) && (reinterpret_cast<uintptr_t>(y) % 8 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0);
+    p.Z = reinterpret_cast<float4 *>(ws + L.off_Z);
+    p.Y = reinterpret_cast<float4 *>(ws + L.off_Y);
+    float4 *H = reinterpret_cast<float4 *>(ws + L.off_H);
+    float4 *tw = reinterpret_cast<float4 *>(ws + L.off_tw);
+    p.H = H;
+    p.tw = tw;
+    p.ctr = reinterpret_cast<unsigned *>(ws);
+    p.trace = (trace_on() && static_cast<size_t>(nitems) <= kTraceItems) ? reinterpret_cast<uint4 *>(ws + L.off_trace) : nullptr;
+
+    TFX_CUDA_TRY(cudaMemsetAsync(ws, 0, kHeaderBytes, stream));
+    if (p.trace != nullptr) TFX_CUDA_TRY(cudaMemsetAsync(p.trace + kTraceItems, 0, 256, stream));
+    fir16k_twiddle_kernel<<<(kTwTotal + 255) / 256, 256, 0, stream>>>(tw);
+    TFX_CHECK_LAUNCH("fir16k_twiddle_kernel");
+    TFX_ENSURE_SMEM(fir16k_taps_kernel, kN * 8);
+    fir16k_taps_kernel<<<static_cast<unsigned>(L.P), kThreads, kN * 8, stream>>>(taps, K, H, tw);
+    TFX_CHECK_LAUNCH("fir16k_taps_kernel");
+    TFX_ENSURE_SMEM(fir16k_kernel, kSmem);
+    {
+        // evict_last only has teeth inside the L2 set-aside for persisting accesses (0 bytes by default)
+        static bool done[64] = {};
+        const int slot = device_slot();
+        if (!done[slot]) {
+            int dev = 0, max_persist = 0;
+            TFX_CUDA_TRY(cudaGetDevice(&dev));
+            TFX_CUDA_TRY(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+            size_t want = static_cast<size_t>(max_persist);
+            if (const char *e = std::getenv("TFX_FIR_PERSIST_MB")) want = std::min(want, static_cast<size_t>(std::atoi(e)) << 20);
+            if (want > 0) TFX_CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+            done[slot] = true;
+        }
+    }
+    const unsigned grid = static_cast<unsigned>(std::min<int64_t>(nitems, sm_count()));
+    fir16k_kernel<<<grid, kThreads, kSmem, stream>>>(p);
+    TFX_CHECK_LAUNCH("fir16k_kernel");
+    return TFX_OK;
+}
+
+}  // namespace tfx
