@@ -34,7 +34,8 @@ CHANNELS = 1024
 SECONDS = float(os.environ.get("TFX_BENCH_SECONDS", "600"))  # override only for local experiments
 SECTIONS = 4
 E2E_SECONDS = float(os.environ.get("TFX_BENCH_E2E_SECONDS", "60"))
-CPU_SAMPLE_SECONDS = float(os.environ.get("TFX_BENCH_CPU_SECONDS", "5"))
+CPU_SAMPLE_SECONDS = float(os.environ.get("TFX_BENCH_CPU_SECONDS", "10"))  # 1024 ch x 10 s slice, best of 3, + a 2x slice
+SECONDARY_SECONDS = float(os.environ.get("TFX_BENCH_SECONDARY_SECONDS", "60"))  # signal length of configs 3-5
 ALGO_BYTES_PER_SAMPLE = 8  # read x f32 once + write y f32 once
 
 
@@ -166,6 +167,228 @@ class ClockSampler:
                 "source": "nvidia-smi -lms 20, timed region only"}
 
 
+def pcie_probe(dev, world: int, nbytes: int = 1 << 30) -> dict:
+    """Pinned-host <-> device copy rates of THIS rank while every rank copies at the same time: the ceiling of
+    the e2e path at this GPU count (1 GiB each way; H2D alone, D2H alone, both at once on two streams)."""
+    import torch
+    import torch.distributed as dist
+
+    n = nbytes // 4
+    h_in = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    h_in.fill_(1.0)
+    h_out = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    d_a = torch.empty(n, dtype=torch.float32, device=dev)
+    d_b = torch.ones(n, dtype=torch.float32, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def h2d():
+        with torch.cuda.stream(s1):
+            d_a.copy_(h_in, non_blocking=True)
+
+    def d2h():
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_b, non_blocking=True)
+
+    def both():
+        h2d()
+        d2h()
+
+    out = {}
+    for name, fn in (("h2d", h2d), ("d2h", d2h), ("duplex_each_way", both)):
+        fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        out[name + "_GBps_per_gpu"] = round(2 * nbytes / float(dt.item()) / 1e9, 2)
+    out["duplex_Gsamples_s_all_gpus"] = round(world * out["duplex_each_way_GBps_per_gpu"] / 4, 2)
+    out["how"] = f"{nbytes >> 20} MiB pinned <-> device per direction and rank, all {world} rank(s) at once, slowest rank"
+    del h_in, h_out, d_a, d_b
+    return out
+
+
+def secondary_configs(dev, world: int, rank: int, peak: float) -> dict:
+    """BASELINE configs 3, 4 and 5 on this GPU count, channels sharded like the headline job; every
+    entry carries its own HBM roofline.  For config 5 also the gathered form of SURVEY.md 8e: kernel only, kernel +
+    chunk-overlapped NCCL all-gather of the output, and the link rate that implies.  An entry that fails reports the
+    error instead of taking the headline line down with it."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import torchfx_b200 as fx
+    from oracle import oracle
+    from torchfx_b200 import _native, _ops
+    from torchfx_b200.dist import all_gather_channels, filter_and_gather, shard_bounds
+
+    T = int(SECONDARY_SECONDS * FS)
+    out: dict = {"seconds": SECONDARY_SECONDS, "n_gpus": world}
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _native.kernel_launches()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), (_native.kernel_launches() - l0) // reps
+
+    def roof(bytes_per_gpu, ms):
+        a = bytes_per_gpu / ms / 1e6
+        return {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "per_gpu": True, "traffic": None}
+
+    def rel(a, b):
+        return float(np.abs(a - b).max() / np.abs(b).max())
+
+    def guarded(name, fn):
+        try:
+            out[name] = fn()
+        except Exception as e:  # keep the headline line alive
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+
+    # ---- config 4: fused pipe chain LoButterworth | ParametricEQ | HiShelving, 2048 channels ---------------
+    def cfg4():
+        C = 2048
+        lo, hi = shard_bounds(C, world, rank)
+        x = torch.empty((hi - lo, T), device=dev).normal_(0, 0.1)
+        mk = lambda: [fx.filter.LoButterworth(5000, order=4, fs=FS), fx.filter.ParametricEQ(1000, q=2.0, gain=3.0, fs=FS),
+                      fx.filter.HiShelving(8000, q=0.707, gain=2.0, gain_scale="db", fs=FS)]
+        chain = mk()
+        ms, nl = timed(lambda: (fx.Wave(x, FS, device=dev) | chain[0] | chain[1] | chain[2]).ys)
+        n_chk = min(T, 1 << 17)
+        y = (fx.Wave(x[:2, :n_chk], FS, device=dev) | chain[0] | chain[1] | chain[2]).ys
+        sos = np.vstack([f._sos.numpy() for f in chain])
+        want, _, _ = oracle.sos_cascade(x[:2, :n_chk].cpu().numpy(), sos)
+        return {"workload": f"fused LoButterworth(5000,4) | ParametricEQ(1000,2,3) | HiShelving(8000,.707,2 dB), {C} ch x {SECONDARY_SECONDS:g} s, TFX_PREC_AUTO",
+                "value": C * T / ms / 1e6, "unit": "Gsamples/s", "ms": ms, "launches_per_call": nl, "channels_per_gpu": hi - lo,
+                "roofline": roof(8.0 * (hi - lo) * T, ms), "parity_rel_err": rel(y.cpu().numpy(), want)}
+
+    # ---- config 5 (stack): LogFilterBank(32) over 256 channels -> [32, 256, T], sharded by channel ----------
+    def cfg5_stack():
+        C, N = 256, 32
+        lo, hi = shard_bounds(C, world, rank)
+        Cr = hi - lo
+        x = torch.empty((Cr, T), device=dev).normal_(0, 0.1)
+        bank = fx.filter.LogFilterBank(n_bands=N, f_min=20.0, f_max=20000.0, q=1.414, fs=FS)
+
+        def run():
+            bank.reset_state()
+            return bank(x)
+
+        ms, nl = timed(run)
+        n_chk = min(T, 1 << 16)
+        bank.reset_state()
+        y = bank(x[:2, :n_chk])
+        want = oracle.filterbank_stack(x[:2, :n_chk].cpu().numpy(), np.stack([f._sos.numpy() for f in bank.filters]))
+        res = {"workload": f"LogFilterBank(32, 20 Hz .. 20 kHz) x {C} ch -> [32, {C}, T] (8192 lanes), {SECONDARY_SECONDS:g} s, TFX_PREC_AUTO",
+               "value": N * C * T / ms / 1e6, "unit": "G lane-samples/s", "ms": ms, "launches_per_call": nl, "channels_per_gpu": Cr,
+               "roofline": roof(4.0 * N * Cr * T * (1 + 1 / N), ms),
+               "parity_rel_err": max(rel(y[b].cpu().numpy(), want[b]) for b in range(N))}
+        del y
+        if world > 1 and C % world == 0:
+            # SURVEY.md 8e: every rank ends up with the whole [32, 256, T].  Time chunks of 1 s; the gather of chunk i
+            # (one all_gather per band plane, rank blocks are contiguous there) runs on a side stream under chunk i + 1.
+            full = torch.empty((N, C, T), dtype=torch.float32, device=dev)
+            comm = torch.cuda.Stream(device=dev)
+            chunk = FS
+            stage = [torch.empty((N, C, chunk), dtype=torch.float32, device=dev) for _ in range(2)]
+
+            def run_gather():
+                bank.reset_state()
+                cur = torch.cuda.current_stream(dev)
+                for i, t0 in enumerate(range(0, T, chunk)):
+                    n = min(chunk, T - t0)
+                    yb = bank(x[:, t0:t0 + n])  # [N, Cr, n], state carried by the bank's children
+                    comm.wait_stream(cur)
+                    with torch.cuda.stream(comm):
+                        st = stage[i % 2][:, :, :n] if n == chunk else torch.empty((N, C, n), dtype=torch.float32, device=dev)
+                        for b in range(N):
+                            dist.all_gather_into_tensor(st[b], yb[b].contiguous())
+                        full[:, :, t0:t0 + n].copy_(st)
+                    yb.record_stream(comm)
+                cur.wait_stream(comm)
+                return full
+
+            g_ms, _ = timed(run_gather, reps=2)
+            recv = 4.0 * N * C * T * (world - 1) / world  # bytes every rank receives over NVLink
+            bank.reset_state()
+            ref = bank(x)
+            got = run_gather()[:, lo:hi]
+            res["gathered"] = {"kernel_only_ms": ms, "kernel_plus_overlapped_all_gather_ms": g_ms, "value": N * C * T / g_ms / 1e6,
+                               "unit": "G lane-samples/s", "bytes_received_per_gpu": recv, "nvlink_GBps_per_gpu": recv / g_ms / 1e6,
+                               "gather_over_kernel": g_ms / ms, "chunk_samples": chunk,
+                               "rel_diff_vs_unchunked": float((got - ref).abs().max() / ref.abs().max())}
+        return res
+
+    # ---- config 5 (sum): parallel `+` biquads -----------------------------------------------------------------
+    def cfg5_sum(nb, C, label):
+        def go():
+            lo, hi = shard_bounds(C, world, rank)
+            x = torch.empty((hi - lo, T), device=dev).normal_(0, 0.1)
+            fl = ([fx.filter.BiquadBPF(200.0 * 1.7 ** i, 1.414, FS) for i in range(nb)] if nb == 8 else
+                  [fx.filter.BiquadBPF(20.0 * (1000.0 ** (i / (nb - 1.0))), 1.414, FS) for i in range(nb)])
+            comb = fx.filter._base.ParallelFilterCombination(*fl)
+
+            def run():
+                for f in fl:
+                    f.reset_state()
+                return comb(x)
+
+            ms, nl = timed(run)
+            n_chk = min(T, 1 << 16)
+            for f in fl:
+                f.reset_state()
+            y = comb(x[:2, :n_chk])
+            want = oracle.filterbank_sum(x[:2, :n_chk].cpu().numpy(), np.stack([f._sos.numpy() for f in fl]))
+            return {"workload": f"{label}: {nb} BiquadBPF added with `+` over {C} ch ({nb * C} biquad lanes), {SECONDARY_SECONDS:g} s, TFX_PREC_AUTO",
+                    "value": C * T / ms / 1e6, "unit": "Gsamples/s", "biquad_lane_value": nb * C * T / ms / 1e6, "ms": ms,
+                    "launches_per_call": nl, "channels_per_gpu": hi - lo, "roofline": roof(8.0 * (hi - lo) * T, ms),
+                    "fma_per_channel_sample": 5 * nb, "parity_rel_err": rel(y.cpu().numpy(), want)}
+        return go
+
+    # ---- config 3: 256-channel overlap-save FIR, 65 536-tap reverb IR --------------------------------------
+    def cfg3():
+        C, K = 256, 65536
+        lo, hi = shard_bounds(C, world, rank)
+        rng = np.random.default_rng(7)
+        ir = rng.standard_normal(K) * np.exp(-np.arange(K) / 8000.0)
+        ir = (ir / np.sqrt((ir ** 2).sum())).astype(np.float32)
+        x = torch.empty((hi - lo, T), device=dev).normal_(0, 0.1)
+        f = fx.filter.FIR(ir)
+        ms, nl = timed(lambda: f(x))
+        n_chk = min(T, 150000)
+        y = f(x[:3, :n_chk])
+        want = oracle.fir_causal(x[:3, :n_chk].cpu().numpy(), ir)
+        r = roof(8.0 * (hi - lo) * T, ms)
+        flops = 2.0 * 130 * (hi - lo) * T  # ~130 fp32 instructions per sample, counted as FMAs (DESIGN.md 4.3)
+        return {"workload": f"FIR overlap-save, 65 536-tap decaying-noise IR, {C} ch x {SECONDARY_SECONDS:g} s",
+                "value": C * T / ms / 1e6, "unit": "Gsamples/s", "ms": ms, "launches_per_call": nl, "channels_per_gpu": hi - lo,
+                "roofline": r, "fp32_TFLOPs_per_gpu_est": flops / ms / 1e9, "note": "fp32-issue bound, not HBM bound (DRAM traffic 10.9 B/sample, profiles/r2_fir.md)",
+                "parity_rel_err": rel(y.cpu().numpy(), want)}
+
+    guarded("cfg4_fused_chain", cfg4)
+    guarded("cfg5_filterbank_stack", cfg5_stack)
+    guarded("cfg5_sum_8x1024", cfg5_sum(8, 1024, "config 5 secondary"))
+    guarded("cfg5_sum_32x256", cfg5_sum(32, 256, "config 5 read literally"))
+    guarded("cfg3_fir_65536", cfg3)
+    return out
+
+
 def reference_cpu_step(ext, x32, sos_t):
     """What the reference does for one filter call on a CPU tensor: up-cast to float64
     (_ops.py:142), fused DF1 cascade in the native extension (iir_cpu.cpp:64-159), cast back
@@ -204,20 +427,25 @@ def cpu_reference_runner():
     return "port", cores, (lambda x32: torch.from_numpy(oracle.sos_cascade(x32.numpy(), sos)[0]))
 
 
-def time_cpu_baseline(sample_seconds: float, reps: int = 1, warm: bool = True):
+def time_cpu_baseline(sample_seconds: float, reps: int = 3, warm: bool = True):
+    """the reference CPU path on a 1024 ch x 10 s slice, best of 3 after a warm-up, plus ONE run of a
+    2x longer slice to confirm that the time scales linearly (so the slice extrapolates to the 10-minute job)."""
     import torch
 
     kind, cores, fn = cpu_reference_runner()
     T = int(sample_seconds * FS)
     g = torch.Generator().manual_seed(1234)
-    x = 0.1 * torch.randn(CHANNELS, T, generator=g)
+    x = 0.1 * torch.randn(CHANNELS, 2 * T, generator=g)
     if warm:
         fn(x[:, : min(T, 4800)])
     best = float("inf")
     for _ in range(reps):
         t0 = time.perf_counter()
-        fn(x)
+        fn(x[:, :T])
         best = min(best, time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    fn(x)
+    t2 = time.perf_counter() - t0
     return {
         "value": CHANNELS * T / best / 1e9,
         "unit": "Gsamples/s",
@@ -225,6 +453,7 @@ def time_cpu_baseline(sample_seconds: float, reps: int = 1, warm: bool = True):
         "kind": kind,
         "sample": f"{CHANNELS} ch x {sample_seconds:g} s @48kHz f32 ({CHANNELS * T / 1e6:.1f} Msamples), f32->f64->f32 casts included, best of {reps}",
         "seconds": best,
+        "linearity": {"slice_2x_seconds": t2, "slice_2x_value": CHANNELS * 2 * T / t2 / 1e9, "time_ratio_2x_over_1x": t2 / best},
     }
 
 
@@ -262,7 +491,8 @@ def run_reference_arm(args) -> None:
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": workload_config(1, reference=True),
+        "config": workload_config(args.gpus),  # key-for-key the dict of the product arm: same workload, same sharding plan
+        "arm_note": "the CPU kernel is timed on a bounded slice of this workload (cpu_baseline.sample); rank 0 only",
         "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -270,7 +500,8 @@ def run_reference_arm(args) -> None:
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus: int, reference: bool = False) -> dict:
+def workload_config(n_gpus: int) -> dict:
+    """The workload both arms are quoted on (identical dict in the product line and the reference line)."""
     cfg = {
         "workload": "BASELINE configs[1]: 1024-ch x 10-min @48kHz float32, 4-section SOS biquad cascade (LoButterworth(5000, order=8))",
         "channels": CHANNELS,
@@ -278,9 +509,6 @@ def workload_config(n_gpus: int, reference: bool = False) -> dict:
         "sections": SECTIONS,
         "fs": FS,
     }
-    if reference:
-        cfg["note"] = "reference arm: CPU kernel timed on a bounded slice of this workload (see cpu_baseline.sample)"
-        return cfg
     cfg.update({
         "channels_per_gpu": CHANNELS // n_gpus,
         "sharding": f"channels over {n_gpus} rank(s), no data-path collective",
@@ -301,6 +529,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip BASELINE configs 3-5 (the `secondary` object)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -417,6 +646,11 @@ def main() -> None:
     # ---- end to end through the host-buffer C-ABI entry (pinned host -> GPU -> pinned host) --
     e2e = None
     if not args.no_e2e:
+        from torchfx_b200.dist import bind_to_gpu_numa_node
+
+        # pinned buffers and the copy-driving thread local to the GPU's PCIe root (round 1: e2e did not scale past ~16)
+        numa = {"skipped": "TFX_BENCH_NO_NUMA"} if os.environ.get("TFX_BENCH_NO_NUMA") else bind_to_gpu_numa_node(local_rank)
+        probe = pcie_probe(dev, world)
         Te = int(E2E_SECONDS * FS)
         xh = torch.empty((C, Te), dtype=torch.float32, pin_memory=True)
         xh.normal_(0.0, 0.1)
@@ -448,8 +682,17 @@ def main() -> None:
             "d2h_bytes_per_step": 4 * CHANNELS * Te,
             "api": "tfx_sos_cascade_host_f32 (pinned host buffers, chunked H2D/kernel/D2H overlap)",
             "sample": f"{CHANNELS} ch x {E2E_SECONDS:g} s slice per step ({e2e_steps} steps), PCIe-bound",
+            "numa_binding_rank0": numa,
+            "pcie_probe": probe,
+            "of_pcie_duplex_ceiling": None,
         }
+        if probe.get("duplex_Gsamples_s_all_gpus"):
+            e2e["of_pcie_duplex_ceiling"] = round(e2e["value"] / probe["duplex_Gsamples_s_all_gpus"], 3)
         del xh, yh
+
+    secondary = None
+    if not args.no_secondary:
+        secondary = secondary_configs(dev, world, rank, peak)
 
     if rank != 0:
         if world > 1:
@@ -480,6 +723,7 @@ def main() -> None:
         "e2e": e2e,
         "gpu_launches": int(nl.item()),
         "parity_rel_err": parity,
+        "secondary": secondary,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

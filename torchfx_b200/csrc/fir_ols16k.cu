@@ -248,7 +248,7 @@ __device__ __forceinline__ p2 *warp_re(unsigned char *smem, int warp) { return r
 
 // v[m] on entry: pair (n = 1024 m + 2 tid, + 1), re = channel a, im = channel b.  `scale` multiplies the result.
 __device__ __forceinline__ void fft16k_fwd(c2 (&v)[16], unsigned char *smem, const float4 *__restrict__ tw,
-                                           float4 *__restrict__ row_out, float scale, PhaseClock &pc, Deferred &df) {
+                                           float4 *__restrict__ row_out, float scale, PhaseClock &pc, Deferred &df, bool stagger = true) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     radix16_dif(v, load_tw(tw + kTw1, tid, 512));
 #pragma unroll
@@ -263,11 +263,11 @@ __device__ __forceinline__ void fft16k_fwd(c2 (&v)[16], unsigned char *smem, con
     p2 *I = R + 512;
     if (warp >= 8) {
         df.flush();
-        half_wait();
+        if (stagger) half_wait();
     }
 #pragma unroll
     for (int m = 0; m < 16; ++m) v[m] = c2{R[m * 32 + lane], I[m * 32 + lane]};
-    if (warp < 8) half_arrive();
+    if (warp < 8 && stagger) half_arrive();
     radix16_dif(v, load_tw(tw + kTw2, lane, 32));
     __syncwarp();
 #pragma unroll
@@ -315,7 +315,7 @@ __device__ __forceinline__ void fft16k_fwd(c2 (&v)[16], unsigned char *smem, con
 // Inverse (unscaled, the 1/N lives in H): row_in in the forward's output order; on return v[m] = pair of time
 // samples (n = 1024 m + 2 tid, + 1).
 __device__ __forceinline__ void fft16k_inv(c2 (&v)[16], unsigned char *smem, const float4 *__restrict__ tw,
-                                           const float4 *__restrict__ row_in, PhaseClock &pc, Deferred &df) {
+                                           const float4 *__restrict__ row_in, PhaseClock &pc, Deferred &df, bool stagger = true) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     p2 *R = warp_re(smem, warp);
     p2 *I = R + 512;
@@ -326,7 +326,7 @@ __device__ __forceinline__ void fft16k_inv(c2 (&v)[16], unsigned char *smem, con
     for (int e = 0; e < 16; ++e) in[e] = ld_keep16(row_in + e * 512 + tid, pol);  // written by other SMs: L2, not L1
     if (warp >= 8) {
         df.flush();
-        half_wait();
+        if (stagger) half_wait();
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -342,7 +342,7 @@ __device__ __forceinline__ void fft16k_inv(c2 (&v)[16], unsigned char *smem, con
         R[o1] = v1.re;
         I[o1] = v1.im;
     }
-    if (warp < 8) half_arrive();
+    if (warp < 8 && stagger) half_arrive();
     __syncwarp();
     pc.lap(6);
 #pragma unroll
@@ -441,6 +441,7 @@ struct Params {
     int npc;       // partition chunks = ceil(P / kPc)
     int nitems;
     int vec_ok;    // rows 8-byte aligned: 64-bit global accesses allowed
+    int stagger;   // bit 0: forward transforms, bit 1: inverse transforms run their two warp halves staggered
     float4 *Z;     // [G][RR][kRowPairs]
     float4 *Y;     // [G][kJ][kRowPairs]
     const float4 *H;  // [P][kRowPairs]
@@ -502,13 +503,13 @@ __device__ __forceinline__ void forward_item(const Params &p, unsigned char *sme
 #pragma unroll
         for (int m = 0; m < 16; ++m) v[m].im = make_float2(0.f, 0.f);
     }
-    fft16k_fwd(v, smem, p.tw, row, 1.0f, pc, df);
+    fft16k_fwd(v, smem, p.tw, row, 1.0f, pc, df, (p.stagger & 1) != 0);
 }
 
 __device__ __forceinline__ void inverse_item(const Params &p, unsigned char *smem, int pair, int k, const float4 *row, PhaseClock &pc, Deferred &df) {
     const int tid = threadIdx.x;
     c2 v[16];
-    fft16k_inv(v, smem, p.tw, row, pc, df);
+    fft16k_inv(v, smem, p.tw, row, pc, df, (p.stagger & 2) != 0);
     const int64_t ca = 2 * static_cast<int64_t>(pair), cb = ca + 1;
     const bool has_b = cb < p.C;
     float *ya = p.y + ca * p.ldy;
@@ -806,6 +807,8 @@ int launch_fir_ols16k(const float *x, float *y, int64_t C, int64_t T, int64_t ld
     // every dependency must sit strictly earlier in the queue: 1 <= LM < LI < G + LM and LM < G
     TFX_REQUIRE(p.LM >= 1 && p.LM < p.LI && p.LI < p.G + p.LM && p.LM < p.G, "fir: bad queue lags LM=%d LI=%d G=%d", p.LM, p.LI, p.G);
     p.RR = L.RR;
+    p.stagger = 3;
+    if (const char *e = std::getenv("TFX_FIR_STAGGER")) p.stagger = std::atoi(e) & 3;
     p.npc = (p.P + kPc - 1) / kPc;
     const int64_t nitems = (NU * p.G + p.LI) * kIpr;
     TFX_REQUIRE(nitems < (int64_t(1) << 31) && NU * kJ < (int64_t(1) << 31), "fir: too many work items for one launch");

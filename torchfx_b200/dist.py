@@ -16,6 +16,42 @@ import torch.distributed as dist
 from torch import Tensor, nn
 
 
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that pinned host buffers allocated
+    afterwards (first touch) and the threads that drive the copies are local to the GPU's PCIe root.
+
+    One process per GPU under ``torchrun`` starts unbound: with 8 ranks streaming host buffers at once, half of
+    the traffic otherwise crosses the socket interconnect (round 1: e2e 11.0 -> 16.2 Gsamples/s from 1 to 8 GPUs).
+    Returns what was done (``{"numa_node": n, "cpus": k}``) or why nothing was (``{"skipped": reason}``); never raises."""
+    import os
+
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bus}"
+        with open(f"{base}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"skipped": "the platform reports no NUMA node for the GPU", "pci": bus}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpulist = f.read().strip()
+        cpus: set[int] = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if not use:
+            return {"skipped": "no allowed CPU on the GPU's NUMA node", "numa_node": node, "pci": bus}
+        os.sched_setaffinity(0, use)
+        return {"numa_node": node, "cpus": len(use), "pci": bus}
+    except Exception as e:  # pragma: no cover - depends on the host
+        return {"skipped": f"{type(e).__name__}: {e}"}
+
+
 def _world(group=None) -> tuple[int, int]:
     if dist.is_available() and dist.is_initialized():
         return dist.get_world_size(group), dist.get_rank(group)
