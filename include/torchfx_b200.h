@@ -70,6 +70,11 @@ extern "C" {
 #define TFX_FORCE_TILE  0x80u /* filterbank: take the lanes = channels kernel (bank_stack) even when */
                               /* its grid would leave most SMs idle and the library would pick the   */
                               /* band-per-lane kernel (small C x T; A/B, tests)                      */
+#define TFX_BANK_STRICT_ORDER 0x100u /* SUM banks of 9..32 children: add the children in child order, as the  */
+                              /* reference's `out += f(x)` loop does (filter/__base.py:1019-1026), on   */
+                              /* the band-per-lane kernel; default = per-warp partial sums (faster,     */
+                              /* rounding-level difference).  Banks of <= 8 children always add in      */
+                              /* child order                                                            */
 #define TFX_NO_SPLIT    0x4u /* never split a channel in time (one sequential stream per     */
                              /* channel; exact for unstable filters; used by tests)          */
 
@@ -190,6 +195,11 @@ size_t tfx_fir_workspace_bytes(int64_t C, int64_t T, int64_t K, int algo);
 int tfx_fir_f32(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
                 const float *taps, int64_t K, int algo,
                 void *workspace, size_t workspace_bytes, void *stream);
+
+/* float64 signals on the device: the reference evaluates the sum in the input dtype
+ * (filter/fir.py:529-531).  Direct form in float64 for every K (no workspace).            */
+int tfx_fir_f64(const double *x, double *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
+                const double *taps, int64_t K, void *stream);
 
 int tfx_fir_cpu_f32(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
                     const float *taps_host, int64_t K);

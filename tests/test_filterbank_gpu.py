@@ -352,6 +352,10 @@ def test_sum_many_bands_vs_oracle(n, kb, C):
     other.flags = _native.TFX_NO_TILE  # band-per-lane kernel: same sum in strict band order
     y2 = other(xt).cpu().numpy()
     assert rel_to_max(y2, y) < 5e-6
+    # TFX_BANK_STRICT_ORDER: the public switch for the reference's child-order sum -- bit-identical to the band-per-lane kernel
+    strict = SosBank(mk(), mode="sum")
+    strict.flags = _native.TFX_BANK_STRICT_ORDER | _native.TFX_FORCE_TILE
+    np.testing.assert_array_equal(strict(xt).cpu().numpy(), y2)
     for i in {0, n // 2, n - 1}:
         _, wsx, wsy = oracle.sos_cascade(x, sos[i])
         np.testing.assert_allclose(filters[i]._state_x.cpu().numpy(), wsx, rtol=1e-6, atol=1e-7)

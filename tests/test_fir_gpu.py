@@ -151,3 +151,22 @@ def test_unaligned_rows_and_views():
     y = fir_causal(x, torch.from_numpy(b), _native.TFX_FIR_OLS)
     want = oracle.fir_causal(x.cpu().numpy(), b)
     assert rel_to_max(y.cpu().numpy(), want) < TOL
+
+
+@pytest.mark.parametrize("K,T,C", [(1, 100, 1), (33, 5000, 3), (512, 4000, 2), (513, 2049, 2), (3000, 10000, 2)])
+def test_float64_signals_are_filtered_in_float64(K, T, C):
+    """The reference evaluates FIR in the input dtype (filter/fir.py:529-531): a float64 CUDA signal runs the float64
+    direct-form kernel (tfx_fir_f64) and must match the float64 oracle to float64 accuracy, not float32's."""
+    rng = np.random.default_rng(K + T)
+    x = rng.standard_normal((C, T))
+    b = rng.standard_normal(K) / np.sqrt(K)
+    import scipy.signal as sps
+
+    want = sps.lfilter(b, [1.0], x, axis=-1)  # float64 direct form, the oracle's FIR entry is float32-I/O
+    y = fir_causal(torch.from_numpy(x).to(DEV), torch.from_numpy(b))
+    assert y.dtype == torch.float64
+    assert rel_to_max(y.cpu().numpy(), want) < 1e-12
+    f = fx.filter.FIR(b.astype(np.float32))  # the module stores float32 taps, like the reference (fir.py:516-518)
+    y2 = f(torch.from_numpy(x).to(DEV))
+    assert y2.dtype == torch.float64
+    assert rel_to_max(y2.cpu().numpy(), sps.lfilter(b.astype(np.float32).astype(np.float64), [1.0], x, axis=-1)) < 1e-12

@@ -231,3 +231,41 @@ def test_mixed_precision_chain_cfg4():
     sty = torch.from_numpy(sy0).to(DEV)
     parts = [_ops.sos_cascade_(xt[:, lo:hi], torch.from_numpy(sos), stx, sty) for lo, hi in ((0, 100000), (100000, 100001), (100001, 400000))]
     assert rel_to_max(torch.cat(parts, 1).cpu().numpy(), want) < 2e-6
+
+
+@pytest.mark.parametrize("where", ["first", "middle", "two"])
+def test_mixed_precision_long_chains(where):
+    """Cascades of 5..8 sections with float32-hostile sections (a 20 Hz high-pass, a narrow low notch): TFX_PREC_AUTO keeps
+    float64 only where it is needed -- any single section or a prefix of sections is instantiated (sos_tile_mixed.cu), other
+    masks are widened to a prefix -- and must meet the float64-recurrence tolerance, state included."""
+    import torchfx_b200 as fx
+    from torchfx_b200 import _native
+
+    lo = fx.filter.LoButterworth(6000, order=6, fs=48000)      # 3 sections, float32-friendly
+    shelf = fx.filter.HiShelving(8000, q=0.707, gain=2.0, gain_scale="db", fs=48000)
+    hp = fx.filter.HiButterworth(20, order=2, fs=48000)        # float32-hostile
+    notch = fx.filter.Notch(60, q=30.0, fs=48000) if hasattr(fx.filter, "Notch") else fx.filter.HiButterworth(30, order=2, fs=48000)
+    eq = fx.filter.ParametricEQ(9000, q=1.0, gain=-2.0, fs=48000)
+    chain = {"first": [hp, lo, shelf, eq], "middle": [lo, hp, shelf, eq], "two": [lo, hp, shelf, notch, eq]}[where]
+    for f in chain:
+        f.compute_coefficients()
+    sos = np.vstack([f._sos.numpy() for f in chain])
+    K = sos.shape[0]
+    assert 5 <= K <= 8
+    lib = _native.load()
+    import ctypes
+
+    err = ctypes.c_double(0.0)
+    mask = lib.tfx_sos_mixed_mask(np.ascontiguousarray(sos).ctypes.data, K, ctypes.byref(err))
+    assert 0 < mask < (1 << K) - 1, f"expected a proper float64 subset, got mask {mask:#x}"
+    rng = np.random.default_rng(11)
+    x = (0.1 * rng.standard_normal((64, 300000))).astype(np.float32)
+    sx0 = 0.1 * rng.standard_normal((K, 64, 2))
+    sy0 = 0.1 * rng.standard_normal((K, 64, 2))
+    want, wsx, wsy = oracle.sos_cascade(x, sos, sx0, sy0)
+    y, sx, sy, _ = run(x, sos, sx0.copy(), sy0.copy(), precision="auto", force_tma=False)
+    assert rel_to_max(y, want) < 2e-6
+    np.testing.assert_allclose(sx, wsx, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(sy, wsy, rtol=1e-4, atol=1e-5 * np.abs(wsy).max())
+    y64, _, _, _ = run(x, sos, sx0.copy(), sy0.copy(), precision="f64", force_tma=False)
+    assert rel_to_max(y, y64) < 2e-6

@@ -27,6 +27,7 @@ TFX_OK = 0
 TFX_EINVAL, TFX_ENODEVICE, TFX_ECUDA, TFX_EWORKSPACE, TFX_ENOMEM = -1, -2, -3, -4, -5
 TFX_PREC_AUTO, TFX_PREC_F32, TFX_PREC_F64, TFX_NO_SPLIT, TFX_NO_TMA, TFX_FORCE_TMA, TFX_PACKED, TFX_NO_TILE = 0, 1, 2, 4, 8, 16, 32, 64
 TFX_FORCE_TILE = 128
+TFX_BANK_STRICT_ORDER = 256
 TFX_BANK_STACK, TFX_BANK_SUM = 0, 1
 TFX_FIR_AUTO, TFX_FIR_DIRECT, TFX_FIR_OLS = 0, 1, 2
 TFX_SOS_MAX_K = 64
@@ -53,6 +54,7 @@ _SIGNATURES = {
     "tfx_filterbank_f64": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, _P, c_int, c_int, c_int, _P, _P, c_uint32, _P, c_size_t, _P]),
     "tfx_fir_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
     "tfx_fir_f32": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64, c_int, _P, c_size_t, _P]),
+    "tfx_fir_f64": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64, _P]),
     "tfx_fir_cpu_f32": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64]),
     "tfx_fir_cpu_f64": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64]),
     "tfx_delay_line_f32": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_double, c_double, _P]),

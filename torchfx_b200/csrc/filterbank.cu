@@ -494,6 +494,7 @@ int filterbank_device(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, int
     if constexpr (sizeof(IO) == 4) {
         // (also SUM banks too large for the register-resident parallel topology above, up to 32 bands)
         bool stack_kernel = (mode == TFX_BANK_STACK || N <= 32) && !(flags & TFX_NO_TILE) && bank_stack_tile_ok(N, Kb, C);
+        if (mode == TFX_BANK_SUM && (flags & TFX_BANK_STRICT_ORDER)) stack_kernel = false;  // child-order sum: band-per-lane kernel
         if (stack_kernel && !(flags & TFX_FORCE_TILE)) {  // enough (channel group x segment x band split) items to fill the GPU?
             int64_t warm_max = 0;
             for (int b = 0; b < std::min(N, 32); ++b) {

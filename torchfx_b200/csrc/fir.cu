@@ -109,6 +109,50 @@ __global__ void __launch_bounds__(256) fir_direct_kernel(const float *__restrict
 }
 
 // ------------------------------------------------------------------------------------------
+// float64 signals: direct form in float64 for every tap count (the reference evaluates FIR in the
+// input dtype, filter/fir.py:529-531).  A CTA owns 1024 outputs of one channel and walks the taps in
+// chunks of 512 through shared memory; 4 consecutive outputs per thread with a register window.
+// O(K T): float64 audio on the device is the rare case, the float32 overlap-save path is the fast one.
+// ------------------------------------------------------------------------------------------
+constexpr int kD64Tile = 1024, kD64Chunk = 512;
+__global__ void __launch_bounds__(256) fir_direct_f64_kernel(const double *__restrict__ x, double *__restrict__ y, int64_t C, int64_t T,
+                                                             int64_t ldx, int64_t ldy, const double *__restrict__ taps, int64_t K,
+                                                             int64_t tiles_per_row) {
+    __shared__ double bs[kD64Chunk];
+    __shared__ double xs[kD64Tile + kD64Chunk];
+    const int64_t c = blockIdx.x / tiles_per_row;
+    const int64_t n0 = (blockIdx.x - c * tiles_per_row) * kD64Tile;
+    const double *xr = x + c * ldx;
+    const int t4 = threadIdx.x * 4;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int64_t j0 = 0; j0 < K; j0 += kD64Chunk) {
+        const int kc = static_cast<int>(min(static_cast<int64_t>(kD64Chunk), K - j0));
+        __syncthreads();
+        for (int i = threadIdx.x; i < kD64Chunk; i += 256) bs[i] = i < kc ? taps[j0 + i] : 0.0;
+        // xs[i] = x[n0 - j0 - (kD64Chunk - 1) + i]: the samples taps j0 .. j0 + 511 pair with outputs n0 .. n0 + 1023
+        for (int i = threadIdx.x; i < kD64Tile + kD64Chunk; i += 256) {
+            const int64_t n = n0 - j0 - (kD64Chunk - 1) + i;
+            xs[i] = (n >= 0 && n < T) ? xr[n] : 0.0;
+        }
+        __syncthreads();
+        // output n0 + t4 + r, tap j0 + u: x[n0 + t4 + r - j0 - u] = xs[(kD64Chunk - 1) + t4 + r - u]
+        const double *w = xs + (kD64Chunk - 1) + t4;
+#pragma unroll 4
+        for (int u = 0; u < kD64Chunk; ++u) {
+            const double b = bs[u];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] = fma(b, w[r - u], acc[r]);
+        }
+    }
+    double *yr = y + c * ldy;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int64_t n = n0 + t4 + r;
+        if (n < T) yr[n] = acc[r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Shared-memory radix-4 FFT (N = 4096 complex, 256 threads, in place)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -940,6 +984,23 @@ int tfx_fir_f32(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int
             fir_inv_r_kernel<4><<<dim3(ninv, npairs), kFftThreads, 0, stream>>>(Y, y, C, T, ldy, k0, nout, tw, twn);
         TFX_CHECK_LAUNCH("fir_inv_kernel");
     }
+    return TFX_OK;
+}
+
+int tfx_fir_f64(const double *x, double *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, const double *taps, int64_t K,
+                void *stream_v) {
+    using namespace tfx;
+    TFX_REQUIRE(C >= 0 && T >= 0, "fir: negative shape");
+    TFX_REQUIRE(K >= 1, "fir: need at least one tap (K=%lld)", (long long)K);
+    if (C == 0 || T == 0) return TFX_OK;
+    TFX_REQUIRE(x != nullptr && y != nullptr && taps != nullptr && x != y, "fir: NULL or aliased buffers (not in place)");
+    TFX_REQUIRE(ldx >= T && ldy >= T, "fir: row stride smaller than T");
+    int rc = require_device();
+    if (rc != TFX_OK) return rc;
+    const int64_t tiles = (T + kD64Tile - 1) / kD64Tile;
+    TFX_REQUIRE(C * tiles < (int64_t(1) << 31), "fir: too many tiles for one launch");
+    fir_direct_f64_kernel<<<static_cast<unsigned>(C * tiles), 256, 0, static_cast<cudaStream_t>(stream_v)>>>(x, y, C, T, ldx, ldy, taps, K, tiles);
+    TFX_CHECK_LAUNCH("fir_direct_f64_kernel");
     return TFX_OK;
 }
 

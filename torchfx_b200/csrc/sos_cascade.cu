@@ -422,9 +422,10 @@ int sos_cascade_device(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, in
         const int64_t pldx = pi == 0 ? ldx : ldy;
         // TFX_PREC_AUTO picked float64 but only some sections need it: mixed-precision tile kernel
         if constexpr (sizeof(IO) == 4) {
-            const unsigned local_mask = static_cast<unsigned>((plan->mixed_mask >> p.k0) & ((1ull << p.k) - 1ull));
+            const unsigned plan_mask = static_cast<unsigned>((plan->mixed_mask >> p.k0) & ((1ull << p.k) - 1ull));
+            const unsigned local_mask = plan_mask == 0u ? 0u : tile_mixed_cover(p.k, plan_mask);  // widened to an instantiated mask
             const bool mixed = (flags & TFX_PREC_MASK) == TFX_PREC_AUTO && plan->auto_prec == TFX_PREC_F64 && !(flags & TFX_NO_TILE) &&
-                               !(flags & TFX_FORCE_TMA) && tile_path_ok(C) && (local_mask == 0u || tile_mixed_supported(p.k, local_mask));
+                               !(flags & TFX_FORCE_TMA) && tile_path_ok(C) && (plan_mask == 0u || local_mask != 0u);
             if (mixed) {
                 const int64_t lanes = (C + 31) / 32 * 32;
                 const Segmentation seg = choose_segmentation(lanes, T, p.warm_f64_io32, tile_stream_capacity(), no_split, kOversub);

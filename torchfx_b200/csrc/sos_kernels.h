@@ -47,6 +47,10 @@ int launch_tile_pass(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, int6
 
 // Mixed precision: float32 recurrence, float64 only in the sections of `f64_mask` (bit k = section k).
 bool tile_mixed_supported(int k, unsigned f64_mask);
+unsigned tile_mixed_cover(int k, unsigned f64_mask);  // smallest instantiated superset of the mask, 0 if none
+int launch_tile_pass_mixed_long(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, const SosSection *sec, int k,
+                                unsigned f64_mask, const Segmentation &seg, void *ws_base, double *state_x, double *state_y,
+                                cudaStream_t stream);  // K = 5..8 (sos_tile_mixed.cu)
 int launch_tile_pass_mixed(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, const SosSection *sec, int k,
                            unsigned f64_mask, const Segmentation &seg, void *ws_base, double *state_x, double *state_y,
                            cudaStream_t stream);

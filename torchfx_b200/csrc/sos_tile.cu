@@ -90,6 +90,7 @@ int launch_tile_pass_mixed(const float *x, float *y, int64_t C, int64_t T, int64
     g.f64_mask = f64_mask;
     g.vec_ok = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0) && ((ldx * 4) % 16 == 0) &&
                ((ldy * 4) % 16 == 0);
+    if (k > 4) return launch_tile_pass_mixed_long(x, y, C, T, ldx, ldy, sec, k, f64_mask, seg, ws_base, state_x, state_y, stream);
     unsigned long long *counter = static_cast<unsigned long long *>(ws_base);
 #define TFX_MIXED_CASE(KK, MM) \
     if (k == KK && f64_mask == MM) return launch_tile_k<float, MixedF<MM>, KK>(sec, g, seg, counter, stream);
@@ -103,7 +104,22 @@ int launch_tile_pass_mixed(const float *x, float *y, int64_t C, int64_t T, int64
     return TFX_EINVAL;
 }
 
-bool tile_mixed_supported(int k, unsigned f64_mask) { return k >= 2 && k <= 4 && f64_mask != 0u && f64_mask != (1u << k) - 1u; }
+bool tile_mixed_supported(int k, unsigned f64_mask) {
+    if (k < 2 || k > 8 || f64_mask == 0u || f64_mask >= (1u << k) - 1u) return false;
+    if (k <= 4) return true;                                  // every proper mask is instantiated (above)
+    if ((f64_mask & (f64_mask - 1u)) == 0u) return true;      // a single section
+    return (f64_mask & (f64_mask + 1u)) == 0u;                // a prefix (sos_tile_mixed.cu)
+}
+
+// Smallest instantiated mask that contains `f64_mask` (0: none short of all sections -> run the float64 kernel).
+unsigned tile_mixed_cover(int k, unsigned f64_mask) {
+    if (tile_mixed_supported(k, f64_mask)) return f64_mask;
+    if (k < 5 || k > 8 || f64_mask == 0u) return 0u;
+    unsigned top = 0;
+    while ((f64_mask >> (top + 1)) != 0u) ++top;              // highest float64 section
+    const unsigned prefix = (2u << top) - 1u;
+    return tile_mixed_supported(k, prefix) ? prefix : 0u;
+}
 
 template int launch_tile_pass<float, float>(const float *, float *, int64_t, int64_t, int64_t, int64_t, const SosSection *, int,
                                             const Segmentation &, void *, double *, double *, cudaStream_t);

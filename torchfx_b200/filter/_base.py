@@ -57,6 +57,9 @@ class ParallelFilterCombination(AbstractFilter):
         super().__init__()
         self.filters = filters
         self._bank = None  # lazily-built fused SOS bank (see _sosbank.py)
+        # True: banks of 9..32 SOS children are added strictly in child order like the reference's loop
+        # (:1019-1026) instead of per-warp partial sums (a rounding-level difference, the default is faster)
+        self.strict_order = False
         self.fs = fs
 
     @property
@@ -88,6 +91,9 @@ class ParallelFilterCombination(AbstractFilter):
         if x.is_cuda and bankable(self.filters):
             if self._bank is None:
                 self._bank = SosBank(self.filters, mode="sum")
+            from .. import _native as N
+
+            self._bank.flags = (self._bank.flags & ~N.TFX_BANK_STRICT_ORDER) | (N.TFX_BANK_STRICT_ORDER if self.strict_order else 0)
             y = self._bank(x)
             if y is not None:
                 return y

@@ -6,8 +6,8 @@ length T; ``conv_mode`` "fft" | "direct" | "auto" :510-514) and ``DesignableFIR`
 (:582-1021: ``scipy.signal.firwin`` :1011-1018).  The reference evaluates the sum with
 ``torch.fft`` overlap-save (filter/_fftconv.py:107-141) or ``F.conv1d``; here both modes
 call the library's own FIR kernels (``tfx_fir_f32``: shared-memory direct form for short
-impulse responses, partitioned overlap-save block FFT for long ones) -- no torch.fft,
-no cuFFT, no conv1d.
+impulse responses, partitioned overlap-save block FFT for long ones; ``tfx_fir_f64``: direct
+form in float64 for float64 signals) -- no torch.fft, no cuFFT, no conv1d.
 """
 from __future__ import annotations
 
@@ -32,14 +32,18 @@ def fir_causal(x: Tensor, taps: Tensor, algo: int = N.TFX_FIR_AUTO) -> Tensor:
     if x.ndim != 2:
         raise ValueError(f"expected [C, T], got {tuple(x.shape)}")
     in_dtype = x.dtype
-    cd = x.dtype if (x.dtype == torch.float64 and not x.is_cuda) else torch.float32
+    cd = x.dtype if x.dtype == torch.float64 else torch.float32  # like the reference: the sum is evaluated in x.dtype
     xw = _ops._rows(x if x.dtype == cd else x.to(cd))
     C, T = xw.shape
     K = taps.numel()
     h = taps.detach().reshape(-1).to(device=xw.device, dtype=cd).contiguous()
     y = torch.empty((C, T), dtype=cd, device=xw.device)
     ldx = xw.stride(0) if C > 1 else max(T, 1)
-    if xw.is_cuda:
+    if xw.is_cuda and cd == torch.float64:
+        with torch.cuda.device(xw.device):
+            N.check(lib.tfx_fir_f64(xw.data_ptr(), y.data_ptr(), C, T, ldx, max(T, 1), h.data_ptr(), K,
+                                    torch.cuda.current_stream(xw.device).cuda_stream))
+    elif xw.is_cuda:
         with torch.cuda.device(xw.device):
             nbytes = lib.tfx_fir_workspace_bytes(C, T, K, algo)
             ws_ptr, ws_bytes = N.workspace(xw.device, nbytes)
