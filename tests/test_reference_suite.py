@@ -21,12 +21,19 @@ import _refsuite_fetch as fetch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
+# One reference test cannot pass with ANY correct implementation, the reference's own included: it compares
+# BiquadHPF(q=0.707) with scipy's Butterworth high-pass (q = 1/sqrt(2) = 0.70710678...) at rtol = atol = 1e-4, and
+# the 1.5e-4 difference in q alone moves ~2 % of the samples by up to 3e-4 (test_unsatisfiable_reference_test_is_
+# unsatisfiable below shows it in exact float64 arithmetic).  The reference's CI never runs it (needs CUDA).
+UNSATISFIABLE = ("test_cuda_kernels.py::TestBiquadCUDA::test_biquad_hpf_matches_scipy",)
+
 
 def _run(files: list[str]) -> tuple[int, dict[str, int], str]:
     d = fetch.tests_dir()
     if d is None:
         pytest.skip("reference test files not available (neither /root/reference nor baseline/_ref/tests)")
     paths = [os.path.join(d, f) for f in files]
+    paths += ["-k", " and ".join("not " + u.rsplit("::", 1)[1] for u in UNSATISFIABLE)]
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, os.path.join(ROOT, "tests"), os.environ.get("PYTHONPATH", "")]))
     cmd = [sys.executable, "-m", "pytest", "-c", os.devnull, "--rootdir", d, "-q", "-p", "_refsuite_plugin",
            "-p", "no:cacheprovider", "--import-mode=importlib", *paths]
@@ -53,4 +60,24 @@ def test_reference_hot_path_files_cuda():
     assert counts.get("failed", 0) == 0, text[-4000:]
     assert counts.get("passed", 0) >= 220, counts
     rc, counts, text = _run(["test_cuda_kernels.py"])
-    assert rc == 0 and counts.get("skipped", 0) == 0 and counts.get("passed", 0) >= 20, text[-4000:]
+    assert rc == 0 and counts.get("skipped", 0) == 0 and counts.get("passed", 0) >= 19, text[-4000:]
+
+
+def test_unsatisfiable_reference_test_is_unsatisfiable():
+    """Why UNSATISFIABLE is deselected: evaluated in exact float64 arithmetic (scipy.lfilter on the q = 0.707 coefficients)
+    the biquad already violates that test's tolerance against scipy's Butterworth for every seed."""
+    import numpy as np
+    from scipy.signal import butter, lfilter
+
+    import torchfx_b200 as fx
+
+    sr = 44100
+    b, a = butter(2, 0.3, btype="high")
+    f = fx.filter.BiquadHPF(cutoff=0.3 * sr / 2, q=0.707, fs=sr)
+    f.compute_coefficients()
+    row = f._sos.numpy()[0]
+    for seed in range(5):
+        x = np.random.default_rng(seed).standard_normal(sr)
+        y_ref = lfilter(b, a, x)
+        y_q = lfilter(row[:3], row[3:], x)
+        assert (np.abs(y_q - y_ref) > 1e-4 + 1e-4 * np.abs(y_ref)).any()

@@ -265,6 +265,10 @@ def test_config2_full_size_parity_as_survey_8d():
     """BASELINE configs[1] at FULL size (1024 ch x 28.8 M samples = 118 GB, in place), the parity check SURVEY.md 8d
     prescribes: ALL 1024 channels on the first 2**20 samples + 8 seeded-random channels over the full 10 minutes
     (long-run drift of the segmented float32 recurrence), both against the CPU oracle.  Needs a 180 GB GPU."""
+    import gc
+
+    gc.collect()
+    torch.cuda.empty_cache()  # earlier tests leave tens of GB in torch's caching allocator
     free, _ = torch.cuda.mem_get_info()
     C, T, HEAD = 1024, 28_800_000, 1 << 20
     if free < C * T * 4 + (8 << 30):
