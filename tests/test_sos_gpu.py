@@ -222,6 +222,25 @@ def test_delay_line_golden():
     assert _ops.delay_line_forward(short, 100, 0.5, 0.5) is short
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("C,T,delay,view", [(3, 10007, 100, False), (2, 4096, 4095, False), (5, 20001, 4410, False), (2, 9001, 7, True),
+                                             (1, 12289, 8192, False), (4, 5000, 1, True)])
+def test_delay_line_shapes_vs_oracle(dtype, C, T, delay, view):
+    """The tiled delay-line kernel against the oracle (delay_cpu.cpp:17-85): delays that are / are not multiples of the
+    vector width, longer than a 4096-sample tile, T not a multiple of the tile, rows that are not 16-byte aligned (view)."""
+    rng = np.random.default_rng(C * T + delay)
+    x = rng.standard_normal((C, T + 1)).astype(dtype)
+    xt = torch.from_numpy(x).to(DEV)
+    xin, xnp = (xt[:, 1:], x[:, 1:]) if view else (xt[:, :T], x[:, :T])
+    y = _ops.delay_line_forward(xin, delay, 0.6, 0.75)
+    want = oracle.delay_line(np.ascontiguousarray(xnp), delay, 0.6, 0.75)
+    assert y.shape == want.shape and y.dtype == xin.dtype
+    if dtype == np.float32:
+        assert rel_to_max(y.cpu().numpy(), want) < 1e-6
+    else:
+        np.testing.assert_allclose(y.cpu().numpy(), want, rtol=1e-13, atol=1e-14)
+
+
 def test_host_streaming_driver_matches_oracle():
     import ctypes
 

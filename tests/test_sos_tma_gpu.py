@@ -236,8 +236,8 @@ def test_mixed_precision_chain_cfg4():
 @pytest.mark.parametrize("where", ["first", "middle", "two"])
 def test_mixed_precision_long_chains(where):
     """Cascades of 5..8 sections with float32-hostile sections (a 20 Hz high-pass, a narrow low notch): TFX_PREC_AUTO keeps
-    float64 only where it is needed -- any single section or a prefix of sections is instantiated (sos_tile_mixed.cu), other
-    masks are widened to a prefix -- and must meet the float64-recurrence tolerance, state included."""
+    float64 only where it is needed -- any single section or the first two are instantiated (sos_tile_mixed.cu), any other
+    mask runs the float64 kernel -- and must meet the float64-recurrence tolerance, state included."""
     import torchfx_b200 as fx
     from torchfx_b200 import _native
 

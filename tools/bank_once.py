@@ -15,7 +15,8 @@ if mode == "stack":
     bank = fx.filter.LogFilterBank(n_bands=N, f_min=20.0, f_max=20000.0, q=1.414, fs=48000)
     run = lambda: (bank.reset_state(), bank(x))[1]
 else:
-    fl = [fx.filter.BiquadBPF(200.0 * 1.7 ** i, 1.414, 48000) for i in range(N)]
+    fl = ([fx.filter.BiquadBPF(200.0 * 1.7 ** i, 1.414, 48000) for i in range(N)] if N <= 8 else
+          [fx.filter.BiquadBPF(20.0 * (1000.0 ** (i / (N - 1.0))), 1.414, 48000) for i in range(N)])  # config 5 read literally
     comb = fx.filter._base.ParallelFilterCombination(*fl)
     def run():
         for f in fl:

@@ -25,6 +25,7 @@
 // scalar epilogue that records each section's DF1 history.
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 
 #include "bank_tile.h"
@@ -324,6 +325,86 @@ __device__ __forceinline__ void band_pair(const StackCoef<KB> &cd, int ba, int b
     }
 }
 
+// 2 * NP float32 bands over one chunk of my row on Blackwell's PACKED fp32 pipe (warm-up and SUM mode): the bands of slots
+// (2q, 2q + 1) share one FFMA2 / FMUL2 per recurrence term -- coefficients and state packed as (band 2q, band 2q + 1), the
+// sample broadcast into both halves.  The scalar pair kernel above is issue-bound (ncu, 32 bands x 256 ch: issue slots 67 %
+// busy with the FMA pipe 50 % active, 27 % of the instructions are not math); packed math halves the issue slots of the math
+// and leaves the FMA pipe as the bound.  The bands' outputs are added in slot order, as everywhere in SUM mode.
+template <int KB, int NP, int OUT>
+__device__ __forceinline__ void band_multi_p(const StackCoef<KB> &cd, const int (&bands)[2 * NP], const unsigned char *xsrc, unsigned char *out,
+                                             double2 *const (&sts)[2 * NP], int lane, int cnt, const int (&lo)[8]) {
+    float2 b0[NP][KB], b1[NP][KB], b2[NP][KB], na1[NP][KB], na2[NP][KB], s1[NP][KB], s2[NP][KB];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const int ba = bands[2 * q], bb = bands[2 * q + 1];
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            b0[q][k] = make_float2(static_cast<float>(cd.b0[ba][k]), static_cast<float>(cd.b0[bb][k]));
+            b1[q][k] = make_float2(static_cast<float>(cd.b1[ba][k]), static_cast<float>(cd.b1[bb][k]));
+            b2[q][k] = make_float2(static_cast<float>(cd.b2[ba][k]), static_cast<float>(cd.b2[bb][k]));
+            na1[q][k] = make_float2(static_cast<float>(-cd.a1[ba][k]), static_cast<float>(-cd.a1[bb][k]));
+            na2[q][k] = make_float2(static_cast<float>(-cd.a2[ba][k]), static_cast<float>(-cd.a2[bb][k]));
+            const double2 sa = sts[2 * q][k * 32 + lane], sb = sts[2 * q + 1][k * 32 + lane];
+            s1[q][k] = make_float2(static_cast<float>(sa.x), static_cast<float>(sb.x));
+            s2[q][k] = make_float2(static_cast<float>(sa.y), static_cast<float>(sb.y));
+        }
+    }
+    auto stepn = [&](float x) -> float {  // returns the slot-ordered sum of the 2 NP band outputs
+        float2 v[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) v[q] = make_float2(x, x);
+#pragma unroll
+        for (int k = 0; k < KB; ++k)
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const float2 y = __ffma2_rn(b0[q][k], v[q], s1[q][k]);
+                s1[q][k] = __ffma2_rn(na1[q][k], y, __ffma2_rn(b1[q][k], v[q], s2[q][k]));
+                s2[q][k] = __ffma2_rn(na2[q][k], y, __fmul2_rn(b2[q][k], v[q]));
+                v[q] = y;
+            }
+        float t = v[0].x + v[0].y;
+#pragma unroll
+        for (int q = 1; q < NP; ++q) t = (t + v[q].x) + v[q].y;
+        return t;
+    };
+    if (cnt == kCH) {
+#pragma unroll
+        for (int v = 0; v < kNV; ++v) {
+            const float4 a = *reinterpret_cast<const float4 *>(xsrc + lo[v & 7] + (v >> 3) * 4096);
+            float4 y;
+            y.x = stepn(a.x);
+            y.y = stepn(a.y);
+            y.z = stepn(a.z);
+            y.w = stepn(a.w);
+            if (OUT == 1) {
+                *reinterpret_cast<float4 *>(out + lo[v & 7] + (v >> 3) * 4096) = y;
+            } else if (OUT == 2) {
+                float4 o = *reinterpret_cast<const float4 *>(out + lo[v & 7] + (v >> 3) * 4096);
+                o.x += y.x;
+                o.y += y.y;
+                o.z += y.z;
+                o.w += y.w;
+                *reinterpret_cast<float4 *>(out + lo[v & 7] + (v >> 3) * 4096) = o;
+            }
+        }
+    } else {
+        for (int e = 0; e < cnt; ++e) {
+            const float y = stepn(*reinterpret_cast<const float *>(xsrc + elem_offset(lane, e)));
+            if (OUT == 1)
+                *reinterpret_cast<float *>(out + elem_offset(lane, e)) = y;
+            else if (OUT == 2)
+                *reinterpret_cast<float *>(out + elem_offset(lane, e)) += y;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q)
+#pragma unroll
+        for (int k = 0; k < KB; ++k) {
+            sts[2 * q][k * 32 + lane] = make_double2(static_cast<double>(s1[q][k].x), static_cast<double>(s2[q][k].x));
+            sts[2 * q + 1][k * 32 + lane] = make_double2(static_cast<double>(s1[q][k].y), static_cast<double>(s2[q][k].y));
+        }
+}
+
 // The last `tail` (<= 2) samples of my channel for one band, straight from / to global memory,
 // recording every section's input / output: that IS the DF1 state handed back.
 template <typename CT, int KB>
@@ -507,6 +588,42 @@ bank_stack_kernel(const __grid_constant__ StackCoef<KB> cd, const __grid_constan
             const bool is64 = (g.f64_mask >> b) & 1u;
             // ---- two bands at once where no per-band output tile is needed (warm-up, SUM) ---------------
             if (warm_pass || g.sum) {
+                // ---- float32 bands: four (or two) at once on packed FFMA2 -------------------------------------------
+                if (!is64 && KB <= 2) {
+                    int nq = 1;  // consecutive float32 slots of this warp whose (warm-up) windows have begun
+                    while (nq < 4 && slot + nq < g.bpw && bl + nq * g.W < nb_cta && (((g.f64_mask >> (b + nq * g.W)) & 1u) == 0u)) ++nq;
+                    if (warm_pass) {
+                        int ok = 0;
+                        while (ok < nq && n0 + base >= max(n1 - static_cast<int64_t>(g.warm_b[b + ok * g.W]), static_cast<int64_t>(0))) ++ok;
+                        nq = ok;
+                    }
+                    if (nq >= 2) {
+                        const int take = nq >= 4 ? 4 : 2;
+                        if (live) {
+                            if (take == 4) {
+                                const int bands[4] = {b, b + g.W, b + 2 * g.W, b + 3 * g.W};
+                                double2 *const sts[4] = {st, st + KB * 32, st + 2 * KB * 32, st + 3 * KB * 32};
+                                if (warm_pass)
+                                    band_multi_p<KB, 2, 0>(cd, bands, tile, nullptr, sts, lane, cnt, lo);
+                                else if (slot == 0)
+                                    band_multi_p<KB, 2, 1>(cd, bands, tile, otile, sts, lane, cnt, lo);
+                                else
+                                    band_multi_p<KB, 2, 2>(cd, bands, tile, otile, sts, lane, cnt, lo);
+                            } else {
+                                const int bands[2] = {b, b + g.W};
+                                double2 *const sts[2] = {st, st + KB * 32};
+                                if (warm_pass)
+                                    band_multi_p<KB, 1, 0>(cd, bands, tile, nullptr, sts, lane, cnt, lo);
+                                else if (slot == 0)
+                                    band_multi_p<KB, 1, 1>(cd, bands, tile, otile, sts, lane, cnt, lo);
+                                else
+                                    band_multi_p<KB, 1, 2>(cd, bands, tile, otile, sts, lane, cnt, lo);
+                            }
+                        }
+                        slot += take - 1;  // the partner slots are done
+                        continue;
+                    }
+                }
                 const int bn = b + g.W;
                 constexpr bool kPair64 = KB <= 2;  // two float64 bands of 3+ sections do not fit the register budget
                 bool pair = slot + 1 < g.bpw && bl + g.W < nb_cta && (((g.f64_mask >> bn) & 1u) != 0u) == is64 && (kPair64 || !is64);

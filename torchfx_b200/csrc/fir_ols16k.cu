@@ -315,7 +315,8 @@ __device__ __forceinline__ void fft16k_fwd(c2 (&v)[16], unsigned char *smem, con
 // Inverse (unscaled, the 1/N lives in H): row_in in the forward's output order; on return v[m] = pair of time
 // samples (n = 1024 m + 2 tid, + 1).
 __device__ __forceinline__ void fft16k_inv(c2 (&v)[16], unsigned char *smem, const float4 *__restrict__ tw,
-                                           const float4 *__restrict__ row_in, PhaseClock &pc, Deferred &df, bool stagger = true) {
+                                           const float4 *__restrict__ row_in, PhaseClock &pc, Deferred &df, bool stagger = true,
+                                           const float4 *__restrict__ taps_row = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     p2 *R = warp_re(smem, warp);
     p2 *I = R + 512;
@@ -324,6 +325,18 @@ __device__ __forceinline__ void fft16k_inv(c2 (&v)[16], unsigned char *smem, con
     const uint64_t pol = policy_evict_last();
 #pragma unroll
     for (int e = 0; e < 16; ++e) in[e] = ld_keep16(row_in + e * 512 + tid, pol);  // written by other SMs: L2, not L1
+    if (taps_row != nullptr) {
+        // Single-partition impulse response (K <= 8192): Y = H . X is a point-wise product, done here on the way in --
+        // no multiply-accumulate items, no product rows.
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const float4 h = __ldg(taps_row + e * 512 + tid);
+            const p2 hr = make_float2(h.x, h.y), hi = make_float2(h.z, h.w);
+            const p2 zr = make_float2(in[e].x, in[e].y), zi = make_float2(in[e].z, in[e].w);
+            const p2 yr = fma2(hr, zr, neg2(mul2(hi, zi))), yi = fma2(hr, zi, mul2(hi, zr));
+            in[e] = make_float4(yr.x, yr.y, yi.x, yi.y);
+        }
+    }
     if (warp >= 8) {
         df.flush();
         if (stagger) half_wait();
@@ -442,6 +455,7 @@ struct Params {
     int nitems;
     int vec_ok;    // rows 8-byte aligned: 64-bit global accesses allowed
     int stagger;   // bit 0: forward transforms, bit 1: inverse transforms run their two warp halves staggered
+    int fuse_p1;   // P == 1: the inverse items multiply by the taps spectrum themselves; MAC items are empty
     float4 *Z;     // [G][RR][kRowPairs]
     float4 *Y;     // [G][kJ][kRowPairs]
     const float4 *H;  // [P][kRowPairs]
@@ -507,9 +521,10 @@ __device__ __forceinline__ void forward_item(const Params &p, unsigned char *sme
 }
 
 __device__ __forceinline__ void inverse_item(const Params &p, unsigned char *smem, int pair, int k, const float4 *row, PhaseClock &pc, Deferred &df) {
+    // (p.fuse_p1: `row` is the block's own spectrum in the ring and the product with H[0] happens on load)
     const int tid = threadIdx.x;
     c2 v[16];
-    fft16k_inv(v, smem, p.tw, row, pc, df, (p.stagger & 2) != 0);
+    fft16k_inv(v, smem, p.tw, row, pc, df, (p.stagger & 2) != 0, p.fuse_p1 ? p.H : nullptr);
     const int64_t ca = 2 * static_cast<int64_t>(pair), cb = ca + 1;
     const bool has_b = cb < p.C;
     float *ya = p.y + ca * p.ldy;
@@ -680,6 +695,7 @@ __global__ void __launch_bounds__(kThreads, 1) fir16k_kernel(const __grid_consta
             type = 2, tile = rho - p.LI, sub = s - kNM - kJ;
         }
         if (tile < 0 || tile >= p.NU * p.G) continue;
+        if (type == 1 && p.fuse_p1) continue;  // single-partition mode has no multiply-accumulate items at all
         if (type == 0 && rho + kPrefetchRounds < p.NU * p.G) {
             // L2 prefetch for the forward item kPrefetchRounds rounds ahead with the same block offset: the NEW half
             // of its input block, 2 channels x 32 KB = one 128-byte line per thread (the old half is the new
@@ -705,7 +721,10 @@ __global__ void __launch_bounds__(kThreads, 1) fir16k_kernel(const __grid_consta
 #define TFX_TRACE_START() do { if (p.trace != nullptr && threadIdx.x == 0) t1 = global_ns(); pk.start(); } while (0)
         if (type == 0) {
             // ring row (u J + sub) overwrites row (u J + sub - RR), last read by the MAC items of tile u - 1
-            wait_count(mdone, static_cast<unsigned>(u) * kNM, df);
+            if (p.fuse_p1)
+                wait_count(idone, static_cast<unsigned>(u > 0 ? u - 1 : 0) * kJ, df);  // ring of 2 J rows: this row was last read by an inverse item of tile u - 2
+            else
+                wait_count(mdone, static_cast<unsigned>(u) * kNM, df);
             TFX_TRACE_START();
             const int k = jt * kJ + sub;
             if (pair_ok && k < p.nblk) {
@@ -719,15 +738,22 @@ __global__ void __launch_bounds__(kThreads, 1) fir16k_kernel(const __grid_consta
             wait_count(fdone, static_cast<unsigned>(u + 1) * kJ, df);  // this tile's (and every earlier tile's) spectra exist
             wait_count(idone, static_cast<unsigned>(u) * kJ, df);      // the previous tile's products have been consumed
             TFX_TRACE_START();
-            if (pair_ok && jt * kJ < p.nblk) mac_item(p, smem, slot, u, jt, sub, pk, df);
+            if (pair_ok && jt * kJ < p.nblk && !p.fuse_p1) mac_item(p, smem, slot, u, jt, sub, pk, df);
             df.flush();
             if (threadIdx.x == kCtl) df.pending = mdone;
             pk.lap(11);
         } else {
-            wait_count(mdone, static_cast<unsigned>(u + 1) * kNM, df);
+            if (p.fuse_p1)
+                wait_count(fdone, static_cast<unsigned>(u + 1) * kJ, df);
+            else
+                wait_count(mdone, static_cast<unsigned>(u + 1) * kNM, df);
             TFX_TRACE_START();
             const int k = jt * kJ + sub;
-            if (pair_ok && k < p.nblk) inverse_item(p, smem, pair, k, p.Y + (static_cast<int64_t>(slot) * kJ + sub) * kRowPairs, pk, df);
+            if (pair_ok && k < p.nblk) {
+                const float4 *row = p.fuse_p1 ? p.Z + (static_cast<int64_t>(slot) * p.RR + (u * kJ + sub) % p.RR) * kRowPairs
+                                              : p.Y + (static_cast<int64_t>(slot) * kJ + sub) * kRowPairs;
+                inverse_item(p, smem, pair, k, row, pk, df);
+            }
             df.flush();
             if (threadIdx.x == kCtl) df.pending = idone;
             pk.lap(12);
@@ -761,6 +787,7 @@ Layout layout16k(int64_t K) {
         if (g >= 4 && g <= kMaxG) L.G = g;
     }
     L.RR = kJ + L.P - 1;
+    if (L.P == 1 && std::getenv("TFX_FIR_NO_FUSE_P1") == nullptr) L.RR = 2 * kJ;  // single-partition mode: the inverse items read the ring, two tiles of rows decouple them from the forward items
     auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
     const size_t row = static_cast<size_t>(kRowPairs) * sizeof(float4);
     L.off_tw = kHeaderBytes;  // counters and the zero row first
@@ -804,6 +831,12 @@ int launch_fir_ols16k(const float *x, float *y, int64_t C, int64_t T, int64_t ld
     p.LI = 8;
     if (const char *e = std::getenv("TFX_FIR_LM")) p.LM = std::atoi(e);
     if (const char *e = std::getenv("TFX_FIR_LI")) p.LI = std::atoi(e);
+    p.fuse_p1 = (p.P == 1 && std::getenv("TFX_FIR_NO_FUSE_P1") == nullptr) ? 1 : 0;
+    if (p.fuse_p1 && std::getenv("TFX_FIR_LM") == nullptr && std::getenv("TFX_FIR_LI") == nullptr) {
+        p.LM = 1;  // there are no MAC items: a round is 64 items, the inverse items follow the forward items ~2 waves later,
+        p.LI = 5;  // and a forward item waits for the inverse items of the previous tile (LI < G keeps that earlier in the queue)
+    }
+    TFX_REQUIRE(!p.fuse_p1 || p.LI < p.G, "fir: single-partition mode needs LI < G (LI=%d G=%d)", p.LI, p.G);
     // every dependency must sit strictly earlier in the queue: 1 <= LM < LI < G + LM and LM < G
     TFX_REQUIRE(p.LM >= 1 && p.LM < p.LI && p.LI < p.G + p.LM && p.LM < p.G, "fir: bad queue lags LM=%d LI=%d G=%d", p.LM, p.LI, p.G);
     p.RR = L.RR;

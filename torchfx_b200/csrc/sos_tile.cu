@@ -108,17 +108,14 @@ bool tile_mixed_supported(int k, unsigned f64_mask) {
     if (k < 2 || k > 8 || f64_mask == 0u || f64_mask >= (1u << k) - 1u) return false;
     if (k <= 4) return true;                                  // every proper mask is instantiated (above)
     if ((f64_mask & (f64_mask - 1u)) == 0u) return true;      // a single section
-    return (f64_mask & (f64_mask + 1u)) == 0u;                // a prefix (sos_tile_mixed.cu)
+    return f64_mask == 3u;                                    // the first two (sos_tile_mixed.cu)
 }
 
 // Smallest instantiated mask that contains `f64_mask` (0: none short of all sections -> run the float64 kernel).
 unsigned tile_mixed_cover(int k, unsigned f64_mask) {
     if (tile_mixed_supported(k, f64_mask)) return f64_mask;
     if (k < 5 || k > 8 || f64_mask == 0u) return 0u;
-    unsigned top = 0;
-    while ((f64_mask >> (top + 1)) != 0u) ++top;              // highest float64 section
-    const unsigned prefix = (2u << top) - 1u;
-    return tile_mixed_supported(k, prefix) ? prefix : 0u;
+    return (f64_mask & ~3u) == 0u ? 3u : 0u;                  // sections 0 and / or 1 -> the first two; anything else: float64 kernel
 }
 
 template int launch_tile_pass<float, float>(const float *, float *, int64_t, int64_t, int64_t, int64_t, const SosSection *, int,
