@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <list>
 #include <mutex>
@@ -324,8 +325,15 @@ Segmentation choose_segmentation(int64_t C, int64_t T, int64_t warm_needed, int6
     S = std::min<int64_t>(S, T / std::max<int64_t>(512, warm));
     if (oversub > 1) {
         // Dynamic scheduling wants several items per resident warp; take them only while the
-        // warm-up stays <= 1/16 of a segment.
-        const int64_t fine = std::min<int64_t>(capacity / C * oversub, T / std::max<int64_t>(4096, 16 * warm));
+        // warm-up stays <= 1/kWarmDiv of a segment: the warm-up launch filters S * warm extra samples per channel.
+        // (1/16 in round 1: the 128-channel shard each of 8 GPUs gets from config 2 then ran 7696 segments of 3742
+        // samples with a 256-sample warm-up; 1/32 measured best on that shard: 5.12 -> 5.05 ms, tools/shard_time.py.)
+        static const int64_t kWarmDiv = [] {
+            const char *e = std::getenv("TFX_WARM_DIV");
+            const int v = e ? std::atoi(e) : 0;
+            return static_cast<int64_t>(v >= 4 && v <= 1024 ? v : 32);
+        }();
+        const int64_t fine = std::min<int64_t>(capacity / C * oversub, T / std::max<int64_t>(4096, kWarmDiv * warm));
         S = std::max(S, fine);
     }
     while (S >= 2) {
