@@ -301,33 +301,34 @@ def secondary_configs(dev, world: int, rank: int, peak: float) -> dict:
                "parity_rel_err": max(rel(y[b].cpu().numpy(), want[b]) for b in range(N))}
         del y
         if world > 1 and C % world == 0:
-            # every rank ends up with the whole [32, 256, T].  Time chunks of 1 s; the gather of chunk i
-            # (one all_gather per band plane, rank blocks are contiguous there) runs on a side stream under chunk i + 1.
+            # every rank ends up with the whole [32, 256, T].  Time chunks of 10 s; the gather of chunk i (one
+            # all_gather of the rank's [32, C/P, n] block + one strided copy into band-major order) runs on a side stream
+            # under the filtering of chunk i + 1.
             torch.cuda.empty_cache()  # the [32, 256, T] result is 94 GB: give the cached blocks of the timing runs back first
             full = torch.empty((N, C, T), dtype=torch.float32, device=dev)
             comm = torch.cuda.Stream(device=dev)
-            chunk = FS
-            stage = [torch.empty((N, C, chunk), dtype=torch.float32, device=dev) for _ in range(2)]
+            chunk = max(FS, T // 6)  # 10 s chunks: long enough for the bank to split a chunk in time (the 20 Hz band forgets in ~0.65 s)
+            stage = torch.empty((world, N, Cr, chunk), dtype=torch.float32, device=dev)  # one buffer: gather and copy-out are ordered on the comm stream
 
             def run_gather():
                 bank.reset_state()
                 cur = torch.cuda.current_stream(dev)
                 for i, t0 in enumerate(range(0, T, chunk)):
                     n = min(chunk, T - t0)
-                    yb = bank(x[:, t0:t0 + n])  # [N, Cr, n], state carried by the bank's children
+                    yb = bank(x[:, t0:t0 + n])  # [N, Cr, n] contiguous, state carried by the bank's children
                     comm.wait_stream(cur)
                     with torch.cuda.stream(comm):
-                        st = stage[i % 2][:, :, :n] if n == chunk else torch.empty((N, C, n), dtype=torch.float32, device=dev)
-                        for b in range(N):
-                            dist.all_gather_into_tensor(st[b], yb[b].contiguous())
-                        full[:, :, t0:t0 + n].copy_(st)
+                        st = stage if n == chunk else torch.empty((world, N, Cr, n), dtype=torch.float32, device=dev)
+                        dist.all_gather_into_tensor(st, yb)  # ONE collective per chunk: every rank's [N, Cr, n] block
+                        # rank-major -> band-major: full[b, r * Cr + c, t0 + t] = st[r, b, c, t]
+                        full[:, :, t0:t0 + n].unflatten(1, (world, Cr)).copy_(st.permute(1, 0, 2, 3))
                     yb.record_stream(comm)
                 cur.wait_stream(comm)
                 return full
 
             g_ms, _ = timed(run_gather, reps=2)
             recv = 4.0 * N * C * T * (world - 1) / world  # bytes every rank receives over NVLink
-            n_cmp = min(T, 5 * chunk)  # compare the first chunks (state is carried across their boundaries) with one unchunked call
+            n_cmp = min(T, chunk + chunk // 2)  # compare across the first chunk boundary (state carried) with one unchunked call
             bank.reset_state()
             ref = bank(x[:, :n_cmp])
             got = run_gather()[:, lo:hi, :n_cmp]
