@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <complex>
 #include <vector>
 
 #include "common.cuh"
@@ -91,11 +92,77 @@ int delay_cpu(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy
 }
 
 // Causal FIR, zero history.  float32 input accumulates in double (one rounding at the end).
+// Short impulse responses: direct form.  Long ones (K > kFirCpuDirectTaps): overlap-save with an in-house double-precision
+// radix-2 FFT, block N >= 4 K, parallel over (channel, block) -- the reference's CPU path is overlap-save too
+// (filter/_fftconv.py:107-141 on torch.fft), a direct form would be O(K T).
+constexpr int64_t kFirCpuDirectTaps = 64;
+
+using cplx = std::complex<double>;
+
+void fft_pow2(cplx *a, int n, const cplx *w /* n/2 roots exp(-2 pi i k / n) */, bool inverse) {
+    for (int i = 1, j = 0; i < n; ++i) {  // bit reversal
+        int bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    for (int len = 2; len <= n; len <<= 1) {
+        const int half = len >> 1, step = n / len;
+        for (int i = 0; i < n; i += len)
+            for (int k = 0; k < half; ++k) {
+                const cplx t = (inverse ? std::conj(w[k * step]) : w[k * step]) * a[i + k + half];
+                a[i + k + half] = a[i + k] - t;
+                a[i + k] += t;
+            }
+    }
+}
+
+template <typename IO>
+void fir_cpu_ols(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, const IO *taps, int64_t K) {
+    int n = 1024;
+    while (n < 4 * K && n < (1 << 22)) n <<= 1;
+    while (n < 2 * K) n <<= 1;  // (only beyond 2^20 taps)
+    const int64_t hop = n - K + 1;
+    const int64_t nblk = (T + hop - 1) / hop;
+    std::vector<cplx> w(n / 2), H(n);
+    for (int k = 0; k < n / 2; ++k) {
+        const double ang = -2.0 * M_PI * k / n;
+        w[k] = cplx(std::cos(ang), std::sin(ang));
+    }
+    for (int64_t i = 0; i < n; ++i) H[i] = i < K ? cplx(static_cast<double>(taps[i]), 0.0) : cplx(0.0, 0.0);
+    fft_pow2(H.data(), n, w.data(), false);
+    const double scale = 1.0 / n;
+#pragma omp parallel
+    {
+        std::vector<cplx> buf(n);
+#pragma omp for collapse(2) schedule(dynamic)
+        for (int64_t c = 0; c < C; ++c)
+            for (int64_t b = 0; b < nblk; ++b) {
+                const IO *xr = x + c * ldx;
+                IO *yr = y + c * ldy;
+                const int64_t s = b * hop;  // first output of the block; input window starts K - 1 samples earlier
+                for (int64_t i = 0; i < n; ++i) {
+                    const int64_t m = s - (K - 1) + i;
+                    buf[i] = (m >= 0 && m < T) ? cplx(static_cast<double>(xr[m]), 0.0) : cplx(0.0, 0.0);
+                }
+                fft_pow2(buf.data(), n, w.data(), false);
+                for (int64_t i = 0; i < n; ++i) buf[i] *= H[i];
+                fft_pow2(buf.data(), n, w.data(), true);
+                const int64_t cnt = std::min<int64_t>(hop, T - s);
+                for (int64_t j = 0; j < cnt; ++j) yr[s + j] = static_cast<IO>(buf[K - 1 + j].real() * scale);
+            }
+    }
+}
+
 template <typename IO>
 int fir_cpu(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, const IO *taps, int64_t K) {
     TFX_REQUIRE(C >= 0 && T >= 0 && K >= 1, "fir (cpu): bad shape");
     if (C == 0 || T == 0) return TFX_OK;
     TFX_REQUIRE(x != nullptr && y != nullptr && taps != nullptr && x != y, "fir (cpu): NULL or aliased buffers");
+    if (K > kFirCpuDirectTaps && T > 2 * K) {
+        fir_cpu_ols<IO>(x, y, C, T, ldx, ldy, taps, K);
+        return TFX_OK;
+    }
     std::vector<double> b(taps, taps + K);
 #pragma omp parallel for schedule(static) if (C > 1)
     for (int64_t c = 0; c < C; ++c) {
