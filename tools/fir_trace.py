@@ -14,6 +14,7 @@ from torchfx_b200 import _native as N  # noqa: E402
 from torchfx_b200.filter.fir import fir_causal  # noqa: E402
 
 DEV = torch.device("cuda:0")
+NCTA = 296 if os.environ.get("TFX_FIR_N") == "8192" else 148  # resident CTAs of the persistent kernel
 
 
 def main(C=256, T=2880000, K=65536):
@@ -42,17 +43,17 @@ def main(C=256, T=2880000, K=65536):
         if not m.any():
             continue
         print(f"  {name:8s} n={m.sum():6d}  run mean {run[m].mean() / 1e3:7.2f} us  median {np.median(run[m]) / 1e3:7.2f}  p95 {np.percentile(run[m], 95) / 1e3:7.2f}"
-              f"  | wait mean {wait[m].mean() / 1e3:7.2f} us  p95 {np.percentile(wait[m], 95) / 1e3:7.2f}  | sum run {run[m].sum() / 1e6 / 148:7.3f} ms/SM  sum wait {wait[m].sum() / 1e6 / 148:7.3f} ms/SM")
+              f"  | wait mean {wait[m].mean() / 1e3:7.2f} us  p95 {np.percentile(wait[m], 95) / 1e3:7.2f}  | sum run {run[m].sum() / 1e6 / NCTA:7.3f} ms/SM  sum wait {wait[m].sum() / 1e6 / NCTA:7.3f} ms/SM")
     idle = (typ >= 0) & (run <= 2000)
-    print(f"  skipped/empty items: {idle.sum()}, their waits sum {wait[idle].sum() / 1e6 / 148:.3f} ms/SM")
+    print(f"  skipped/empty items: {idle.sum()}, their waits sum {wait[idle].sum() / 1e6 / NCTA:.3f} ms/SM")
     names = ["mac wait+barrier", "mac issue", "mac compute+store", "fwd load+P1+barrier", "fwd P2+P3", "fwd P4+store", "inv load+P4", "inv P3+P2",
              "inv barrier", "inv P1+store", "fwd signal", "mac signal", "inv signal"]
     n_by = {"mac": (typ == 1).sum(), "fwd": (typ == 0).sum(), "inv": (typ == 2).sum()}
     print("  phase clocks (thread 0, cycles per item of that type):")
     for i, nm in enumerate(names):
         print(f"    {nm:22s} {ph[i] / max(n_by[nm[:3]], 1):9.0f}")
-    busy = run.sum() / (148 * span)
-    print(f"  busy fraction (run / (148 x span)) = {busy:.3f}, waiting fraction = {wait.sum() / (148 * span):.3f}")
+    busy = run.sum() / (NCTA * span)
+    print(f"  busy fraction (run / (CTAs x span)) = {busy:.3f}, waiting fraction = {wait.sum() / (NCTA * span):.3f}")
 
 
 if __name__ == "__main__":
