@@ -58,13 +58,10 @@ extern "C" {
                              /* else f64 recurrence (hard part 1)               */
 #define TFX_PREC_F32    0x1u /* force float32 recurrence (f32 I/O only)                      */
 #define TFX_PREC_F64    0x2u /* force float64 recurrence (what the reference computes in)    */
-#define TFX_NO_TMA      0x8u  /* cascade kernel choice: never / always (where eligible, see        */
-#define TFX_FORCE_TMA   0x10u /* tfx_sos_cascade_uses_tma) take the TMA-tiled kernel; neither =   */
-                              /* the default cp.async tile kernel, measured faster in every case  */
-                              /* on B200 (A/B timing, tests)                                      */
-#define TFX_PACKED      0x20u /* float32 recurrence: opt in to the packed-pair FFMA2 kernel (two   */
-                              /* streams per thread); measured slower than the scalar kernel on   */
-                              /* B200, kept for A/B timing and tests                  */
+#define TFX_NO_TMA      0x8u  /* RESERVED, accepted and ignored: round 1 shipped a TMA-tiled and a  */
+#define TFX_FORCE_TMA   0x10u /* packed-pair (FFMA2) cascade kernel behind these bits; both lost    */
+#define TFX_PACKED      0x20u /* every A/B against the cp.async tile kernel on B200 and were removed */
+                              /* (profiles/r1_experiments.md sections 3, 4, 12 keep the record)     */
 #define TFX_NO_TILE     0x40u /* never take the channel-tile kernel (lanes = channels); use the    */
                               /* stream-per-lane kernel even for many channels (A/B, tests)       */
 #define TFX_FORCE_TILE  0x80u /* filterbank: take the lanes = channels kernel (bank_stack) even when */
@@ -121,13 +118,6 @@ int tfx_sos_cascade_f64(const double *x, double *y, int64_t C, int64_t T,
                         double *state_x, double *state_y,
                         uint32_t flags, void *workspace, size_t workspace_bytes,
                         void *stream);
-
-/* 1 when a call with these arguments is ELIGIBLE for the TMA-tiled kernel
- * (cp.async.bulk.tensor tiles of 32 channels x 64 samples): enough channels to fill the
- * lanes, 16-byte aligned rows, T < 2^31.  0: only the generic cp.async kernel applies.
- * elem_bytes is 4 or 8.                                                                   */
-int tfx_sos_cascade_uses_tma(const void *x, const void *y, int64_t C, int64_t T,
-                             int64_t ldx, int64_t ldy, int elem_bytes);
 
 /* What TFX_PREC_AUTO resolves to for this cascade: returns TFX_PREC_F32 or TFX_PREC_F64,
  * and (optionally) the probe's estimated f32 round-off relative to max|y|.               */
@@ -195,6 +185,20 @@ size_t tfx_fir_workspace_bytes(int64_t C, int64_t T, int64_t K, int algo);
 int tfx_fir_f32(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
                 const float *taps, int64_t K, int algo,
                 void *workspace, size_t workspace_bytes, void *stream);
+
+/* Plan for the overlap-save algorithm: everything that depends on the impulse response only
+ * (FFT twiddle tables and the spectra of the K-tap response's partitions) computed ONCE into
+ * a caller-owned, 16-byte aligned DEVICE buffer of tfx_fir_plan_bytes(K) bytes, so that
+ * chunked callers (a FIR module called per audio block) do not transform the taps on every
+ * call.  The reference keeps its flipped kernel as a module buffer (filter/fir.py:516-518)
+ * and re-runs rfft(kernel) inside every fft_conv1d call (filter/_fftconv.py:124).
+ * tfx_fir_f32_planned == tfx_fir_f32 with algo TFX_FIR_OLS and the same workspace
+ * (tfx_fir_workspace_bytes(C, T, K, TFX_FIR_OLS)); results are bit-identical.             */
+size_t tfx_fir_plan_bytes(int64_t K);
+int tfx_fir_plan_init(const float *taps, int64_t K, void *plan, size_t plan_bytes, void *stream);
+int tfx_fir_f32_planned(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
+                        const void *plan, int64_t K,
+                        void *workspace, size_t workspace_bytes, void *stream);
 
 /* float64 signals on the device: the reference evaluates the sum in the input dtype
  * (filter/fir.py:529-531).  Direct form in float64 for every K (no workspace).            */

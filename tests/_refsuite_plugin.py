@@ -44,3 +44,14 @@ _install()
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "benchmark: reference marker (unused here)")
+
+
+def pytest_runtest_setup(item):
+    """Several reference tests draw their input from numpy's unseeded global generator.  One of them
+    (test_cuda_kernels.py::TestBiquadCUDA::test_biquad_lpf_matches_scipy, q = 0.707 against scipy's q = 1/sqrt(2) at
+    1e-4) is marginal: in exact float64 arithmetic 28 % of the draws violate its tolerance
+    (tests/test_reference_suite.py::test_marginal_reference_test_depends_on_the_draw).  Seeding the global generator
+    per test makes every run see the same draw."""
+    import numpy as np
+
+    np.random.seed(0)

@@ -13,7 +13,7 @@ from conftest import golden, rel_to_max
 from oracle import oracle
 from torchfx_b200 import _native
 from torchfx_b200.filter._fftconv import fft_conv1d
-from torchfx_b200.filter.fir import fir_causal
+from torchfx_b200.filter.fir import fir_causal, fir_plan
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -80,6 +80,33 @@ def test_partition_edges(K, T):
     assert rel_to_max(y.cpu().numpy(), want) < TOL
 
 
+@pytest.mark.parametrize("K", [300, 8192, 20000, 65536])
+def test_plan_is_bit_identical_and_cached(K):
+    """tfx_fir_plan_init + tfx_fir_f32_planned (twiddles and taps spectra computed once) against tfx_fir_f32 with
+    TFX_FIR_OLS, bit for bit; the FIR module builds the plan on its first call and reuses it for later chunks, and a
+    changed kernel buffer (in-place edit bumps the tensor version) invalidates it."""
+    rng = np.random.default_rng(K)
+    b = (rng.standard_normal(K) * np.exp(-np.arange(K) / (K / 5.0))).astype(np.float32)
+    x = torch.from_numpy(rng.standard_normal((6, 50000)).astype(np.float32)).to(DEV)
+    bt = torch.from_numpy(b).to(DEV)
+    y0 = fir_causal(x, bt, _native.TFX_FIR_OLS)
+    plan = fir_plan(bt)
+    y1 = fir_causal(x, bt, _native.TFX_FIR_OLS, plan=plan)
+    assert torch.equal(y0, y1)
+    f = fx.filter.FIR(b).to(DEV)
+    n0 = _native.load().tfx_kernel_launches()
+    ya = f(x)
+    n1 = _native.load().tfx_kernel_launches()
+    yb = f(x[:, :30000])
+    n2 = _native.load().tfx_kernel_launches()
+    if K > 96:  # overlap-save (AUTO takes the direct form below 97 taps)
+        assert n1 - n0 == 3 and n2 - n1 == 1, (n1 - n0, n2 - n1)  # plan (2 kernels) + filter, then the filter alone
+    assert torch.equal(ya, y0) and torch.equal(yb, fir_causal(x[:, :30000], bt, _native.TFX_FIR_OLS))
+    f.kernel.mul_(2.0)
+    yc = f(x)
+    assert rel_to_max(yc.cpu().numpy(), 2.0 * y0.cpu().numpy()) < 1e-6
+
+
 def test_cfg3_reverb_ir_65536_taps():
     """BASELINE configs[2] at oracle-checkable size: 65 536-tap decaying-noise IR,
     5 channels (odd: one half-empty pair) x 100 000 samples."""
@@ -124,13 +151,11 @@ def test_shapes_and_dtype_like_reference():
         fx.filter.FIR(b, conv_mode="nope")
 
 
-@pytest.mark.parametrize("knobs", [{}, {"TFX_FIR_G": "4", "TFX_FIR_LM": "1", "TFX_FIR_LI": "2"}, {"TFX_FIR_G": "12", "TFX_FIR_LM": "5", "TFX_FIR_LI": "10"},
-                                   {"TFX_FIR_V1": "1"}])
+@pytest.mark.parametrize("knobs", [{}, {"TFX_FIR_G": "4", "TFX_FIR_LM": "1", "TFX_FIR_LI": "2"}, {"TFX_FIR_G": "12", "TFX_FIR_LM": "5", "TFX_FIR_LI": "10"}])
 @pytest.mark.parametrize("K,T,C", [(3000, 20000, 3), (9000, 50001, 2), (33000, 70000, 5), (65536, 40000, 1), (100000, 300000, 19)])
-def test_queue_settings_and_first_version(knobs, K, T, C, monkeypatch):
+def test_queue_settings(knobs, K, T, C, monkeypatch):
     """The persistent overlap-save kernel under different queue settings (open channel-pair slots G, queue lags of the
-    multiply and inverse items: the schedule changes, the result must not) and the first three-kernel implementation
-    (TFX_FIR_V1); odd channel counts leave a half-empty pair, T is not a multiple of the 8192-sample hop, K is not a
+    multiply and inverse items: the schedule changes, the result must not); odd channel counts leave a half-empty pair, T is not a multiple of the 8192-sample hop, K is not a
     multiple of the partition, 19 channels need more than one group of slots."""
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)

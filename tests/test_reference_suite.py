@@ -81,3 +81,29 @@ def test_unsatisfiable_reference_test_is_unsatisfiable():
         y_ref = lfilter(b, a, x)
         y_q = lfilter(row[:3], row[3:], x)
         assert (np.abs(y_q - y_ref) > 1e-4 + 1e-4 * np.abs(y_ref)).any()
+
+
+def test_marginal_reference_test_depends_on_the_draw():
+    """Why tests/_refsuite_plugin.py seeds numpy before each reference test: the low-pass twin of the deselected test
+    (test_biquad_lpf_matches_scipy, unseeded np.random.randn) sits ON its tolerance -- the exact float64 evaluation of
+    the q = 0.707 design passes for some draws and fails for others (about 28 % of them), whatever computes it."""
+    import numpy as np
+    from scipy.signal import butter, lfilter
+
+    import torchfx_b200 as fx
+
+    sr = 44100
+    b, a = butter(2, 0.1)
+    f = fx.filter.BiquadLPF(cutoff=0.1 * sr / 2, q=0.707, fs=sr)
+    f.compute_coefficients()
+    row = f._sos.numpy()[0]
+    verdicts = []
+    for seed in range(40):
+        x = np.random.default_rng(seed).standard_normal(sr)
+        y_ref = lfilter(b, a, x)
+        verdicts.append(bool((np.abs(lfilter(row[:3], row[3:], x) - y_ref) <= 1e-4 + 1e-4 * np.abs(y_ref)).all()))
+    assert any(verdicts) and not all(verdicts), verdicts
+    np.random.seed(0)  # the draw the runner pins: passes, by 5e-6
+    x = np.random.randn(1, sr)
+    y_ref = lfilter(b, a, x)
+    assert (np.abs(lfilter(row[:3], row[3:], x) - y_ref) <= 1e-4 + 1e-4 * np.abs(y_ref)).all()

@@ -1,6 +1,6 @@
-"""GPU parity of the TMA-tiled cascade kernel (sos_tma.cu) -- the path every BASELINE
-config takes (many channels, aligned rows) -- against the oracle, and A/B against the
-generic cp.async kernel (TFX_NO_TMA) on the same inputs."""
+"""GPU parity of the channel-tile cascade kernel (sos_tile.cu: lanes = 32 consecutive channels, cp.async tiles) -- the
+path every BASELINE config takes (>= 26 channels) -- against the oracle, and A/B against the stream-per-lane kernel
+(TFX_NO_TILE) on the same inputs; float64 I/O; the mixed-precision instantiations."""
 from __future__ import annotations
 
 import numpy as np
@@ -18,28 +18,14 @@ TOL_F32 = 1e-5
 TOL_F64REC = 1e-6
 
 
-def uses_tma(x, y=None):
-    y = x if y is None else y
-    return bool(_native.load().tfx_sos_cascade_uses_tma(x.data_ptr(), y.data_ptr(), x.shape[0], x.shape[1], x.stride(0), y.stride(0), x.element_size()))
-
-
 def run(x_np, sos_np, sx=None, sy=None, **kw):
     x = torch.from_numpy(np.ascontiguousarray(x_np)).to(DEV)
     K, C = sos_np.shape[0], x.shape[0]
     stx = torch.zeros(K, C, 2, dtype=torch.float64, device=DEV) if sx is None else torch.from_numpy(sx).to(DEV)
     sty = torch.zeros(K, C, 2, dtype=torch.float64, device=DEV) if sy is None else torch.from_numpy(sy).to(DEV)
-    kw.setdefault("force_tma", not kw.get("no_tma", False))
     y = _ops.sos_cascade_(x, torch.from_numpy(sos_np), stx, sty, **kw)
     torch.cuda.synchronize()
     return y.cpu().numpy(), stx.cpu().numpy(), sty.cpu().numpy(), x
-
-
-def test_path_selection():
-    a = torch.zeros(64, 4096, device=DEV)
-    assert uses_tma(a)
-    assert not uses_tma(torch.zeros(2, 4096, device=DEV))  # too few channels for channel-per-lane
-    assert not uses_tma(torch.zeros(64, 4099, device=DEV))  # rows not 16-byte aligned
-    assert uses_tma(torch.zeros(64, 4096, dtype=torch.float64, device=DEV))
 
 
 @pytest.mark.parametrize("K", [1, 2, 3, 4, 5, 6, 7, 8, 12])
@@ -50,7 +36,6 @@ def test_every_section_count(K):
     want, wsx, wsy = oracle.sos_cascade(x, sos)
     for precision, tol in (("f32", TOL_F32), ("f64", TOL_F64REC)):
         y, sx, sy, xt = run(x, sos, precision=precision)
-        assert uses_tma(xt)
         assert rel_to_max(y, want) < tol, (K, precision)
         np.testing.assert_allclose(sx, wsx, rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(sy, wsy, rtol=1e-3, atol=tol * 10 * max(np.abs(wsy).max(), 1e-30))
@@ -67,7 +52,6 @@ def test_short_and_ragged_with_state(shape):
     sy0 = rng.standard_normal((2, shape[0], 2))
     want, wsx, wsy = oracle.sos_cascade(x, sos, sx0, sy0)
     y, sx, sy, xt = run(x, sos, sx0.copy(), sy0.copy(), precision="f64")
-    assert uses_tma(xt)
     assert rel_to_max(y, want) < TOL_F64REC
     np.testing.assert_allclose(sx, wsx, rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(sy, wsy, rtol=1e-5, atol=1e-5)
@@ -80,10 +64,7 @@ def test_time_split_many_channels_matches_generic_and_oracle():
     pick = [0, 31, 32, 63]
     want, _, wsy = oracle.sos_cascade(x[pick], sos)
     y_t, _, sy_t, _ = run(x, sos, precision="f32")
-    y_g, _, sy_g, _ = run(x, sos, precision="f32", no_tma=True, no_tile=True)  # stream-per-lane kernel
-    y_c, _, sy_c, _ = run(x, sos, precision="f32", no_tma=True)                # channel-tile kernel
-    assert rel_to_max(y_c[pick], want) < TOL_F32 and rel_to_max(y_c, y_g) < 2e-6
-    np.testing.assert_allclose(sy_c, sy_g, rtol=1e-4, atol=1e-6 * np.abs(wsy).max())
+    y_g, _, sy_g, _ = run(x, sos, precision="f32", no_tile=True)  # stream-per-lane kernel; y_t: channel-tile kernel
     y_n, _, _, _ = run(x, sos, precision="f32", no_split=True)
     assert rel_to_max(y_t[pick], want) < TOL_F32
     assert rel_to_max(y_g[pick], want) < TOL_F32
@@ -103,7 +84,7 @@ def test_chunked_stream_and_in_place():
     sy = torch.zeros_like(sx)
     for lo, hi in ((0, 30000), (30000, 30004), (30004, 100000)):
         blk = xt[:, lo:hi]
-        _ops.sos_cascade_(blk, sos, sx, sy, out=blk, force_tma=True)  # in place on a strided view
+        _ops.sos_cascade_(blk, sos, sx, sy, out=blk)  # in place on a strided view
     assert rel_to_max(xt.cpu().numpy(), want) < TOL_F32
     np.testing.assert_allclose(sy.cpu().numpy(), wsy, rtol=1e-3, atol=1e-5 * np.abs(wsy).max())
 
@@ -117,7 +98,6 @@ def test_f64_io():
     sy0 = rng.standard_normal((3, 52, 2))
     want, wsx, wsy = oracle.sos_cascade(x, sos, sx0, sy0)
     y, sx, sy, xt = run(x, sos, sx0.copy(), sy0.copy())
-    assert uses_tma(xt)
     np.testing.assert_allclose(y, want, rtol=1e-9, atol=1e-10)
     np.testing.assert_allclose(sx, wsx, rtol=1e-9, atol=1e-10)
     np.testing.assert_allclose(sy, wsy, rtol=1e-9, atol=1e-10)
@@ -129,31 +109,12 @@ def test_out_of_place_keeps_input():
     sos = sps.butter(4, 0.2, output="sos")
     want, _, _ = oracle.sos_cascade(x, sos)
     xt = torch.from_numpy(x).to(DEV)
-    y = _ops.sos_cascade_(xt, torch.from_numpy(sos), None, None, force_tma=True)
+    y = _ops.sos_cascade_(xt, torch.from_numpy(sos), None, None)
     assert torch.equal(xt.cpu(), torch.from_numpy(x))
     assert rel_to_max(y.cpu().numpy(), want) < TOL_F32
 
 
-@pytest.mark.parametrize("K", [1, 4, 8])
-def test_packed_ffma2_kernel_matches(K):
-    """Opt-in packed-pair (FFMA2) kernel: two streams per thread."""
-    rng = np.random.default_rng(500 + K)
-    x = (0.1 * rng.standard_normal((37, 150001))).astype(np.float32)  # odd T: ragged rows; 37 ch: half-empty tiles
-    sos = sps.butter(2 * K, 0.21, output="sos")
-    sx0 = rng.standard_normal((K, 37, 2)) * 0.1
-    sy0 = rng.standard_normal((K, 37, 2)) * 0.1
-    want, wsx, wsy = oracle.sos_cascade(x, sos, sx0, sy0)
-    y, sx, sy, _ = run(x, sos, sx0.copy(), sy0.copy(), precision="f32", packed=True, no_tma=True)
-    assert rel_to_max(y, want) < TOL_F32
-    np.testing.assert_allclose(sx, wsx, rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(sy, wsy, rtol=1e-3, atol=1e-4 * max(np.abs(wsy).max(), 1e-30))
-    xa = (0.1 * rng.standard_normal((64, 1 << 18))).astype(np.float32)
-    wa, _, _ = oracle.sos_cascade(xa[:4], sos)
-    ya, _, _, _ = run(xa, sos, precision="f32", packed=True, no_tma=True)
-    assert rel_to_max(ya[:4], wa) < TOL_F32
-
-
-# ---- channel-tile kernel (sos_tile.cu), the default for many channels -------------------------------
+# ---- more shapes: odd T, unaligned rows, long cascades, strided views -------------------------------
 @pytest.mark.parametrize("shape", [(32, 1), (32, 2), (32, 3), (64, 63), (64, 64), (64, 65), (96, 129), (128, 1000), (52, 260),
                                    (27, 2052), (33, 4099), (100, 777)])
 @pytest.mark.parametrize("precision", ["f32", "f64"])
@@ -166,7 +127,7 @@ def test_tile_kernel_short_ragged_with_state(shape, precision):
     sx0 = rng.standard_normal((2, shape[0], 2))
     sy0 = rng.standard_normal((2, shape[0], 2))
     want, wsx, wsy = oracle.sos_cascade(x, sos, sx0, sy0)
-    y, sx, sy, _ = run(x, sos, sx0.copy(), sy0.copy(), precision=precision, no_tma=True)
+    y, sx, sy, _ = run(x, sos, sx0.copy(), sy0.copy(), precision=precision)
     tol = TOL_F32 if precision == "f32" else TOL_F64REC
     assert rel_to_max(y, want) < tol
     np.testing.assert_allclose(sx, wsx, rtol=1e-6, atol=1e-6)
@@ -179,12 +140,12 @@ def test_tile_kernel_section_counts_and_f64_io(K):
     x = rng.standard_normal((40, 30000))
     sos = sps.butter(2 * K, 0.23, output="sos")
     want, wsx, wsy = oracle.sos_cascade(x, sos)
-    y, sx, sy, _ = run(x, sos, no_tma=True)  # float64 I/O through the tile kernel
+    y, sx, sy, _ = run(x, sos)  # float64 I/O through the tile kernel
     np.testing.assert_allclose(y, want, rtol=1e-8, atol=1e-10)
     np.testing.assert_allclose(sy, wsy, rtol=1e-8, atol=1e-10)
     xf = x.astype(np.float32)
     wf, _, _ = oracle.sos_cascade(xf, sos)
-    yf, _, _, _ = run(xf, sos, precision="f32", no_tma=True)
+    yf, _, _, _ = run(xf, sos, precision="f32")
     assert rel_to_max(yf, wf) < TOL_F32
 
 
@@ -200,7 +161,7 @@ def test_tile_kernel_chunked_in_place_strided_view():
     sy = torch.zeros_like(sx)
     for lo, hi in ((0, 40000), (40000, 40004), (40004, 100000)):
         blk = view[:, lo:hi]
-        _ops.sos_cascade_(blk, sos, sx, sy, out=blk, no_tma=True)
+        _ops.sos_cascade_(blk, sos, sx, sy, out=blk)
     assert rel_to_max(view.cpu().numpy(), want) < TOL_F32
     np.testing.assert_allclose(sy.cpu().numpy(), wsy, rtol=1e-3, atol=1e-5 * np.abs(wsy).max())
     assert torch.equal(big[0], torch.from_numpy((0.1 * np.random.default_rng(77).standard_normal((70, 120000))).astype(np.float32))[0].to(DEV))
@@ -221,7 +182,7 @@ def test_mixed_precision_chain_cfg4():
     sx0 = 0.1 * rng.standard_normal((4, 64, 2))
     sy0 = 0.1 * rng.standard_normal((4, 64, 2))
     want, wsx, wsy = oracle.sos_cascade(x, sos, sx0, sy0)
-    y, sx, sy, _ = run(x, sos, sx0.copy(), sy0.copy(), precision="auto", force_tma=False)
+    y, sx, sy, _ = run(x, sos, sx0.copy(), sy0.copy(), precision="auto")
     assert rel_to_max(y, want) < 2e-6
     np.testing.assert_allclose(sx, wsx, rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(sy, wsy, rtol=1e-4, atol=1e-5 * np.abs(wsy).max())
@@ -263,9 +224,9 @@ def test_mixed_precision_long_chains(where):
     sx0 = 0.1 * rng.standard_normal((K, 64, 2))
     sy0 = 0.1 * rng.standard_normal((K, 64, 2))
     want, wsx, wsy = oracle.sos_cascade(x, sos, sx0, sy0)
-    y, sx, sy, _ = run(x, sos, sx0.copy(), sy0.copy(), precision="auto", force_tma=False)
+    y, sx, sy, _ = run(x, sos, sx0.copy(), sy0.copy(), precision="auto")
     assert rel_to_max(y, want) < 2e-6
     np.testing.assert_allclose(sx, wsx, rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(sy, wsy, rtol=1e-4, atol=1e-5 * np.abs(wsy).max())
-    y64, _, _, _ = run(x, sos, sx0.copy(), sy0.copy(), precision="f64", force_tma=False)
+    y64, _, _, _ = run(x, sos, sx0.copy(), sy0.copy(), precision="f64")
     assert rel_to_max(y, y64) < 2e-6

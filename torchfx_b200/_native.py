@@ -45,7 +45,6 @@ _SIGNATURES = {
     "tfx_sos_cascade_f64": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int, _P, _P, c_uint32, _P, c_size_t, _P]),
     "tfx_sos_auto_precision": (c_int, [_P, c_int, _P]),
     "tfx_sos_mixed_mask": (c_uint64, [_P, c_int, _P]),
-    "tfx_sos_cascade_uses_tma": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int]),
     "tfx_sos_cascade_cpu_f32": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int, _P, _P]),
     "tfx_sos_cascade_cpu_f64": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int, _P, _P]),
     "tfx_sos_cascade_host_f32": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int, _P, _P, c_uint32, c_int64, c_int]),
@@ -55,6 +54,9 @@ _SIGNATURES = {
     "tfx_fir_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
     "tfx_fir_f32": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64, c_int, _P, c_size_t, _P]),
     "tfx_fir_f64": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64, _P]),
+    "tfx_fir_plan_bytes": (c_size_t, [c_int64]),
+    "tfx_fir_plan_init": (c_int, [_P, c_int64, _P, c_size_t, _P]),
+    "tfx_fir_f32_planned": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64, _P, c_size_t, _P]),
     "tfx_fir_cpu_f32": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64]),
     "tfx_fir_cpu_f64": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64]),
     "tfx_delay_line_f32": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, c_double, c_double, _P]),

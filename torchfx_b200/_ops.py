@@ -101,9 +101,6 @@ def sos_cascade_(
     out: Tensor | None = None,
     precision: str | None = None,
     no_split: bool = False,
-    no_tma: bool = False,
-    force_tma: bool = False,
-    packed: bool = False,
     no_tile: bool = False,
 ) -> Tensor:
     """Fused K-section cascade over ``x`` ``[C, T]``; updates ``state_x`` / ``state_y``
@@ -146,7 +143,7 @@ def sos_cascade_(
         xw, ldx, ldy = y, ldp, ldp
     if xw.is_cuda:
         flags = (_PRECISIONS[precision or _default_precision] | (N.TFX_NO_SPLIT if no_split else 0)
-                 | (N.TFX_NO_TMA if no_tma else 0) | (N.TFX_FORCE_TMA if force_tma else 0) | (N.TFX_PACKED if packed else 0) | (N.TFX_NO_TILE if no_tile else 0))
+                 | (N.TFX_NO_TILE if no_tile else 0))
         with _device_guard(xw):
             nbytes = lib.tfx_sos_cascade_workspace_bytes(C, T, K)
             ws_ptr, ws_bytes = N.workspace(xw.device, nbytes)

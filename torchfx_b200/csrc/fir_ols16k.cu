@@ -803,8 +803,37 @@ Layout layout16k(int64_t K) {
 
 size_t fir_ols16k_workspace_bytes(int64_t K) { return layout16k(K).total; }
 
-int launch_fir_ols16k(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, const float *taps, int64_t K,
-                      void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+// A plan = what depends on the impulse response only: [twiddle tables | pad to 256 B | H[P] rows].
+namespace {
+size_t plan_off_H() { return (sizeof(float4) * kTwTotal + 255) & ~size_t(255); }
+int fill_plan(const float *taps, int64_t K, float4 *tw, float4 *H, cudaStream_t stream) {
+    const int64_t P = (K + kB - 1) / kB;
+    TFX_REQUIRE(P >= 1 && P < (int64_t(1) << 20), "fir: impulse response of %lld taps is out of range", (long long)K);
+    fir16k_twiddle_kernel<<<(kTwTotal + 255) / 256, 256, 0, stream>>>(tw);
+    TFX_CHECK_LAUNCH("fir16k_twiddle_kernel");
+    TFX_ENSURE_SMEM(fir16k_taps_kernel, kN * 8);
+    fir16k_taps_kernel<<<static_cast<unsigned>(P), kThreads, kN * 8, stream>>>(taps, K, H, tw);
+    TFX_CHECK_LAUNCH("fir16k_taps_kernel");
+    return TFX_OK;
+}
+}  // namespace
+
+size_t fir_ols16k_plan_bytes(int64_t K) {
+    const int64_t P = (K + kB - 1) / kB;
+    return plan_off_H() + static_cast<size_t>(kRowPairs) * sizeof(float4) * static_cast<size_t>(P);
+}
+
+int fir_ols16k_plan_init(const float *taps, int64_t K, void *plan, size_t plan_bytes, cudaStream_t stream) {
+    if (plan == nullptr || plan_bytes < fir_ols16k_plan_bytes(K) || reinterpret_cast<uintptr_t>(plan) % 16 != 0) {
+        set_error("fir plan: a 16-byte aligned buffer of %zu bytes is needed, %zu given (query tfx_fir_plan_bytes)", fir_ols16k_plan_bytes(K), plan_bytes);
+        return TFX_EWORKSPACE;
+    }
+    unsigned char *pb = static_cast<unsigned char *>(plan);
+    return fill_plan(taps, K, reinterpret_cast<float4 *>(pb), reinterpret_cast<float4 *>(pb + plan_off_H()), stream);
+}
+
+int launch_fir_ols16k(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, const float *taps, const void *plan,
+                      int64_t K, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
     const Layout L = layout16k(K);
     if (workspace == nullptr || workspace_bytes < L.total) {
         set_error("fir: workspace of %zu bytes needed, %zu given (query tfx_fir_workspace_bytes)", L.total, workspace_bytes);
@@ -850,20 +879,23 @@ int launch_fir_ols16k(const float *x, float *y, int64_t C, int64_t T, int64_t ld
     p.vec_ok = (reinterpret_cast<uintptr_t>(x) % 8 == 0) && (reinterpret_cast<uintptr_t>(y) % 8 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0);
     p.Z = reinterpret_cast<float4 *>(ws + L.off_Z);
     p.Y = reinterpret_cast<float4 *>(ws + L.off_Y);
-    float4 *H = reinterpret_cast<float4 *>(ws + L.off_H);
-    float4 *tw = reinterpret_cast<float4 *>(ws + L.off_tw);
-    p.H = H;
-    p.tw = tw;
+    if (plan != nullptr) {  // twiddles and taps spectra were computed once by fir_ols16k_plan_init
+        const unsigned char *pb = static_cast<const unsigned char *>(plan);
+        p.tw = reinterpret_cast<const float4 *>(pb);
+        p.H = reinterpret_cast<const float4 *>(pb + plan_off_H());
+    } else {
+        p.tw = reinterpret_cast<const float4 *>(ws + L.off_tw);
+        p.H = reinterpret_cast<const float4 *>(ws + L.off_H);
+    }
     p.ctr = reinterpret_cast<unsigned *>(ws);
     p.trace = (trace_on() && static_cast<size_t>(nitems) <= kTraceItems) ? reinterpret_cast<uint4 *>(ws + L.off_trace) : nullptr;
 
     TFX_CUDA_TRY(cudaMemsetAsync(ws, 0, kHeaderBytes, stream));
     if (p.trace != nullptr) TFX_CUDA_TRY(cudaMemsetAsync(p.trace + kTraceItems, 0, 256, stream));
-    fir16k_twiddle_kernel<<<(kTwTotal + 255) / 256, 256, 0, stream>>>(tw);
-    TFX_CHECK_LAUNCH("fir16k_twiddle_kernel");
-    TFX_ENSURE_SMEM(fir16k_taps_kernel, kN * 8);
-    fir16k_taps_kernel<<<static_cast<unsigned>(L.P), kThreads, kN * 8, stream>>>(taps, K, H, tw);
-    TFX_CHECK_LAUNCH("fir16k_taps_kernel");
+    if (plan == nullptr) {
+        const int rc = fill_plan(taps, K, reinterpret_cast<float4 *>(ws + L.off_tw), reinterpret_cast<float4 *>(ws + L.off_H), stream);
+        if (rc != TFX_OK) return rc;
+    }
     TFX_ENSURE_SMEM(fir16k_kernel, kSmem);
     {
         // evict_last only has teeth inside the L2 set-aside for persisting accesses (0 bytes by default)

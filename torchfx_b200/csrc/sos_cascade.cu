@@ -380,18 +380,6 @@ int launch_pass(const SosSection *sec, int k, const Geom &g, const Segmentation 
     }
 }
 
-// Kernel choice.  The TMA tile path is capped near 4.6 TB/s by the per-SM TMA request rate on DRAM-missing
-// 128-byte rows (profiles/r1_experiments.md section 3).  While the cp.async tile kernel still read its tiles with
-// generic loads, TMA won the heavy cases (float64, K >= 6) and the dispatcher took it there; with LDS/STS tile
-// accesses the cp.async kernel is faster everywhere (1024 ch x 60 s, Gsamples/s, tile vs TMA: f64 K=4 625 vs 487,
-// f64 K=6 466 vs 366, f32 K=6 694 vs 527, f32 K=8 525 vs 489), so TMA now runs only on request (TFX_FORCE_TMA).
-bool want_tma(uint32_t flags, uint32_t prec, int k) {
-    (void)prec;
-    (void)k;
-    if (flags & TFX_NO_TMA) return false;
-    return (flags & TFX_FORCE_TMA) != 0;
-}
-
 int64_t stream_capacity() { return static_cast<int64_t>(sm_count()) * kWarpsPerSm * 32; }
 
 template <typename IO>
@@ -425,7 +413,7 @@ int sos_cascade_device(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, in
             const unsigned plan_mask = static_cast<unsigned>((plan->mixed_mask >> p.k0) & ((1ull << p.k) - 1ull));
             const unsigned local_mask = plan_mask == 0u ? 0u : tile_mixed_cover(p.k, plan_mask);  // widened to an instantiated mask
             const bool mixed = (flags & TFX_PREC_MASK) == TFX_PREC_AUTO && plan->auto_prec == TFX_PREC_F64 && !(flags & TFX_NO_TILE) &&
-                               !(flags & TFX_FORCE_TMA) && tile_path_ok(C) && (plan_mask == 0u || local_mask != 0u);
+                               tile_path_ok(C) && (plan_mask == 0u || local_mask != 0u);
             if (mixed) {
                 const int64_t lanes = (C + 31) / 32 * 32;
                 const Segmentation seg = choose_segmentation(lanes, T, p.warm_f64_io32, tile_stream_capacity(), no_split, kOversub);
@@ -447,33 +435,7 @@ int sos_cascade_device(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, in
                 continue;
             }
         }
-        if (want_tma(flags, prec, p.k) && tma_path_ok(px, y, C, T, pldx, ldy, sizeof(IO))) {
-            // TMA-tiled kernel: a warp is 32 consecutive channels, so segments are counted per
-            // channel GROUP (capacity / 32 warps in one wave).
-            const int64_t lanes = (C + 31) / 32 * 32;
-            const Segmentation seg = choose_segmentation(lanes, T, warm_needed, tma_stream_capacity(), no_split);
-            if (seg.S > 1) {
-                const size_t need = static_cast<size_t>(2 * p.k) * static_cast<size_t>(C * seg.S) * (prec == TFX_PREC_F32 ? 4 : 8);
-                if (workspace == nullptr || workspace_bytes < need) {
-                    set_error("sos cascade: workspace of %zu bytes needed, %zu given (query tfx_sos_cascade_workspace_bytes)", need,
-                              workspace_bytes);
-                    return TFX_EWORKSPACE;
-                }
-            }
-            double *psx = state_x ? state_x + static_cast<int64_t>(p.k0) * C * 2 : nullptr;
-            double *psy = state_y ? state_y + static_cast<int64_t>(p.k0) * C * 2 : nullptr;
-            if (prec == TFX_PREC_F32) {
-                if constexpr (sizeof(IO) == 4)
-                    rc = launch_tma_pass<IO, float>(px, y, C, T, pldx, ldy, plan->sec.data() + p.k0, p.k, seg, workspace, psx, psy, stream);
-                else
-                    rc = TFX_EINVAL;
-            } else {
-                rc = launch_tma_pass<IO, double>(px, y, C, T, pldx, ldy, plan->sec.data() + p.k0, p.k, seg, workspace, psx, psy, stream);
-            }
-            if (rc != TFX_OK) return rc;
-            continue;
-        }
-        if (!(flags & TFX_NO_TILE) && !(flags & TFX_PACKED) && tile_path_ok(C)) {
+        if (!(flags & TFX_NO_TILE) && tile_path_ok(C)) {
             // channel-tile kernel: a warp is 32 consecutive channels x one time segment
             const int64_t lanes = (C + 31) / 32 * 32;
             const Segmentation seg = choose_segmentation(lanes, T, warm_needed, tile_stream_capacity(), no_split, kOversub);
@@ -498,10 +460,8 @@ int sos_cascade_device(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, in
             if (rc != TFX_OK) return rc;
             continue;
         }
-        // opt-in: float32 recurrence on the packed FP32 pipe (FFMA2), two streams per thread
-        const bool packed = sizeof(IO) == 4 && prec == TFX_PREC_F32 && (flags & TFX_PACKED);
-        const Segmentation seg =
-            choose_segmentation(C, T, warm_needed, packed ? packed_stream_capacity() : stream_capacity(), no_split, kOversub);
+        // stream-per-lane kernel (few channels, or on request)
+        const Segmentation seg = choose_segmentation(C, T, warm_needed, stream_capacity(), no_split, kOversub);
         Geom g{};
         g.x = pi == 0 ? static_cast<const void *>(x) : static_cast<const void *>(y);
         g.y = y;
@@ -528,9 +488,7 @@ int sos_cascade_device(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, in
                 return TFX_EWORKSPACE;
             }
         }
-        if (packed) {
-            rc = launch_packed_pass(plan->sec.data() + p.k0, p.k, g, seg, stream);
-        } else if (prec == TFX_PREC_F32) {
+        if (prec == TFX_PREC_F32) {
             if constexpr (sizeof(IO) == 4) {
                 rc = launch_pass<IO, float>(plan->sec.data() + p.k0, p.k, g, seg, stream);
             } else {
@@ -553,8 +511,7 @@ size_t tfx_sos_cascade_workspace_bytes(int64_t C, int64_t T, int K) {
     (void)T;
     if (C <= 0 || K <= 0) return 0;
     // S > 1 only when C*S <= one wave of streams; state is 2 values per fused section.
-    const int64_t streams = std::max<int64_t>(std::max(std::max(tfx::stream_capacity(), tfx::packed_stream_capacity()), tfx::tile_stream_capacity()) * tfx::kOversub,
-                                              tfx::tma_stream_capacity()) + C + 128;
+    const int64_t streams = std::max<int64_t>(tfx::stream_capacity(), tfx::tile_stream_capacity()) * tfx::kOversub + C + 128;
     const int kf = K < TFX_SOS_MAX_FUSED ? K : TFX_SOS_MAX_FUSED;
     return tfx::kWsHeader + static_cast<size_t>(2 * kf) * static_cast<size_t>(streams) * 8 + 256;
 }
@@ -578,11 +535,6 @@ uint64_t tfx_sos_mixed_mask(const double *sos_host, int K, double *mixed_rel_err
     if (!plan) return 0;
     if (mixed_rel_err) *mixed_rel_err = plan->mixed_rel_err;
     return plan->auto_prec == TFX_PREC_F64 ? plan->mixed_mask : 0;
-}
-
-int tfx_sos_cascade_uses_tma(const void *x, const void *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, int elem_bytes) {
-    if (tfx::require_device() != TFX_OK) return 0;
-    return tfx::tma_path_ok(x, y, C, T, ldx, ldy, elem_bytes) ? 1 : 0;
 }
 
 int tfx_sos_auto_precision(const double *sos_host, int K, double *probe_rel_err) {

@@ -1,4 +1,4 @@
-// sos_kernels.h -- entry points of the two cascade kernels (sos_tma.cu, sos_cascade.cu).
+// sos_kernels.h -- entry points of the cascade kernels (sos_cascade.cu: stream per lane; sos_tile.cu: lanes = channels).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -15,7 +15,7 @@ constexpr size_t kWsHeader = 256;  // workspace header (work counter)
 #endif
 constexpr int kOversub = TFX_OVERSUB;  // work items per resident warp when the signal is long enough
 
-// Launch geometry shared by the cp.async stream kernels (sos_cascade.cu, sos_packed.cu).
+// Launch geometry of the stream-per-lane kernel (sos_cascade.cu).
 struct Geom {
     const void *x;
     void *y;
@@ -34,10 +34,6 @@ struct Geom {
 };
 
 
-// Packed-pair kernel (sos_packed.cu): float32 only, two streams per thread on FFMA2.
-int64_t packed_stream_capacity();
-int launch_packed_pass(const SosSection *sec, int k, Geom g, const Segmentation &seg, cudaStream_t stream);
-
 // Channel-tile kernel (sos_tile.cu): lanes = 32 consecutive channels, cp.async tiles.
 bool tile_path_ok(int64_t C);
 int64_t tile_stream_capacity();
@@ -54,12 +50,5 @@ int launch_tile_pass_mixed_long(const float *x, float *y, int64_t C, int64_t T, 
 int launch_tile_pass_mixed(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, const SosSection *sec, int k,
                            unsigned f64_mask, const Segmentation &seg, void *ws_base, double *state_x, double *state_y,
                            cudaStream_t stream);
-
-// TMA-tiled kernel (sos_tma.cu): lanes = 32 consecutive channels.
-bool tma_path_ok(const void *x, const void *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, int elem_bytes);
-int64_t tma_stream_capacity();  // streams (lanes) resident in one wave
-template <typename IO, typename CT>
-int launch_tma_pass(const IO *x, IO *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, const SosSection *sec, int k,
-                    const Segmentation &seg, void *ws, double *state_x, double *state_y, cudaStream_t stream);
 
 }  // namespace tfx

@@ -11,9 +11,9 @@
 //   stored with a 128-byte XOR swizzle (16-byte column v of row r lives at column v^(r&7))
 //   so lane r reading "its" row with 128-bit LDS/STS is bank-conflict free without padding;
 //   filtered in place; written back with coalesced 128-bit streaming stores.
-// The same tile layout is what sos_tma.cu moves with cp.async.bulk.tensor; on B200 the TMA
-// variant is capped near 4.6 TB/s by the per-SM TMA request rate on DRAM-missing 128-byte
-// rows (profiles/), the LDGSTS variant is not, so this one is the default.
+// Round 1 also moved the same tiles with cp.async.bulk.tensor (TMA): on B200 that variant is
+// capped near 4.6 TB/s by the per-SM TMA request rate on DRAM-missing 128-byte rows
+// (profiles/r1_experiments.md section 3), the LDGSTS variant is not; the TMA kernel was removed.
 //
 // Work distribution: persistent warps pull (channel group, segment) items from a global
 // counter; segment start states come from a warm-up launch (see sos_plan.cpp).

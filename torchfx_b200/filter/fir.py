@@ -26,8 +26,28 @@ from ._base import AbstractFilter
 _ALGO = {"fft": N.TFX_FIR_AUTO, "auto": N.TFX_FIR_AUTO, "direct": N.TFX_FIR_DIRECT}
 
 
-def fir_causal(x: Tensor, taps: Tensor, algo: int = N.TFX_FIR_AUTO) -> Tensor:
-    """y[c, n] = sum_j taps[j] * x[c, n - j] over ``x`` ``[C, T]`` (zero history)."""
+_DIRECT_MAX_TAPS = 96  # TFX_FIR_AUTO takes the direct form up to here (csrc/fir.cu kAutoDirectTaps)
+
+
+def fir_plan(taps: Tensor) -> Tensor:
+    """Overlap-save plan of a float32 impulse response on a CUDA device (``tfx_fir_plan_init``): the FFT twiddle tables
+    and the spectra of the taps' partitions, computed once.  The reference re-runs ``rfft(kernel)`` inside every
+    ``fft_conv1d`` call (filter/_fftconv.py:124)."""
+    lib = N.load()
+    h = taps.detach().reshape(-1).to(dtype=torch.float32).contiguous()
+    if not h.is_cuda:
+        raise ValueError("fir_plan needs the taps on a CUDA device")
+    K = h.numel()
+    nbytes = lib.tfx_fir_plan_bytes(K)
+    plan = torch.empty(nbytes, dtype=torch.uint8, device=h.device)
+    with torch.cuda.device(h.device):
+        N.check(lib.tfx_fir_plan_init(h.data_ptr(), K, plan.data_ptr(), nbytes, torch.cuda.current_stream(h.device).cuda_stream))
+    return plan
+
+
+def fir_causal(x: Tensor, taps: Tensor, algo: int = N.TFX_FIR_AUTO, plan: Tensor | None = None) -> Tensor:
+    """y[c, n] = sum_j taps[j] * x[c, n - j] over ``x`` ``[C, T]`` (zero history).  ``plan``: a ``fir_plan(taps)`` made
+    on ``x``'s device; float32 CUDA signals then take the overlap-save kernel without transforming the taps again."""
     lib = N.load()
     if x.ndim != 2:
         raise ValueError(f"expected [C, T], got {tuple(x.shape)}")
@@ -36,13 +56,24 @@ def fir_causal(x: Tensor, taps: Tensor, algo: int = N.TFX_FIR_AUTO) -> Tensor:
     xw = _ops._rows(x if x.dtype == cd else x.to(cd))
     C, T = xw.shape
     K = taps.numel()
-    h = taps.detach().reshape(-1).to(device=xw.device, dtype=cd).contiguous()
+    use_plan = plan is not None and xw.is_cuda and cd == torch.float32
+    h = None if use_plan else taps.detach().reshape(-1).to(device=xw.device, dtype=cd).contiguous()
     y = torch.empty((C, T), dtype=cd, device=xw.device)
     ldx = xw.stride(0) if C > 1 else max(T, 1)
     if xw.is_cuda and cd == torch.float64:
         with torch.cuda.device(xw.device):
             N.check(lib.tfx_fir_f64(xw.data_ptr(), y.data_ptr(), C, T, ldx, max(T, 1), h.data_ptr(), K,
                                     torch.cuda.current_stream(xw.device).cuda_stream))
+    elif use_plan:
+        if plan.device != xw.device or plan.numel() < lib.tfx_fir_plan_bytes(K):
+            raise ValueError("plan was made for another device or a longer impulse response")
+        with torch.cuda.device(xw.device):
+            nbytes = lib.tfx_fir_workspace_bytes(C, T, K, N.TFX_FIR_OLS)
+            ws_ptr, ws_bytes = N.workspace(xw.device, nbytes)
+            N.check(
+                lib.tfx_fir_f32_planned(xw.data_ptr(), y.data_ptr(), C, T, ldx, max(T, 1), plan.data_ptr(), K, ws_ptr, ws_bytes,
+                                        torch.cuda.current_stream(xw.device).cuda_stream)
+            )
     elif xw.is_cuda:
         with torch.cuda.device(xw.device):
             nbytes = lib.tfx_fir_workspace_bytes(C, T, K, algo)
@@ -67,6 +98,8 @@ class FIR(AbstractFilter):
         self.a = [1.0]
         # same buffer name / layout as the reference so state_dicts stay interchangeable
         self.register_buffer("kernel", taps.flip(0)[None, None, :])
+        self._plan: Tensor | None = None   # overlap-save plan of the current kernel on the device it was last used on
+        self._plan_key: tuple | None = None
 
     def compute_coefficients(self) -> None:
         pass
@@ -83,7 +116,18 @@ class FIR(AbstractFilter):
         else:
             raise ValueError("Input must be of shape [T], [C, T], or [B, C, T]")
         taps = self.kernel[0, 0].flip(0)  # natural order b[0..K)
-        return fir_causal(x2, taps, _ALGO[self._conv_mode]).reshape(shape)
+        algo = _ALGO[self._conv_mode]
+        plan = None
+        K = taps.numel()
+        if x2.is_cuda and x2.dtype != torch.float64 and x2.numel() > 0 and (K > 1024 or (algo == N.TFX_FIR_AUTO and K > _DIRECT_MAX_TAPS)):
+            # the overlap-save kernel will run: reuse the taps' spectra across calls (chunked callers); keyed by the
+            # buffer's identity and version, so load_state_dict / in-place edits / .to() rebuild it
+            key = (self.kernel.data_ptr(), self.kernel._version, K, x2.device)
+            if self._plan_key != key:
+                self._plan = fir_plan(taps.to(x2.device))
+                self._plan_key = key
+            plan = self._plan
+        return fir_causal(x2, taps, algo, plan=plan).reshape(shape)
 
 
 class DesignableFIR(FIR):
