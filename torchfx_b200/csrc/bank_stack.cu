@@ -806,6 +806,133 @@ int ctas_per_sm(int W, int bpw, int KB) {
     return std::max(1, std::min(std::min(n, by_threads), kMaxCtas));
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Time-parallel warm-up for single-section bands (KB == 1: LogFilterBank, sums of biquads).
+//
+// The warm-up launch above gives a band's whole decay window to ONE lane-row per channel: the 20 Hz band of a
+// LogFilterBank(32) needs 31 k samples, i.e. one float64 dependency chain of 31 k steps per (channel group, segment)
+// while the other warps of the CTA have long finished -- 1.08 ms of the 3.6 ms the 32-channel shard of config 5 takes.
+// A biquad is linear, so the window can be cut into 32 pieces that run in parallel from a ZERO state: with the free-
+// response matrix A = [[-a1, 1], [-a2, 0]] of the DF2T state (s1, s2),
+//     state(n1) = sum_p A^(n1 - end_p) z_p,        z_p = zero-state end state of piece p.
+// One warp per (channel, band, segment): lane p filters piece p = [n1 - (p + 1) Lp, n1 - p Lp) of the channel
+// (16-byte loads of its own stretch of the row; each 128-byte line is fetched once and then served by L1), raises A to
+// p * Lp by repeated squaring in float64, and a fixed-order shuffle tree adds the 32 contributions (deterministic).
+// The piece that contains sample 0 starts from the caller's DF1 state instead of zero, as the serial warm-up does.
+// Critical path: Lp = warm / 32 samples instead of warm.
+// ------------------------------------------------------------------------------------------------------------
+struct M22 {
+    double a, b, c, d;  // [[a, b], [c, d]]
+};
+__device__ __forceinline__ M22 mmul(const M22 &x, const M22 &y) {
+    return M22{__fma_rn(x.a, y.a, x.b * y.c), __fma_rn(x.a, y.b, x.b * y.d), __fma_rn(x.c, y.a, x.d * y.c), __fma_rn(x.c, y.b, x.d * y.d)};
+}
+template <typename CT>
+__device__ __forceinline__ void warm1_run(const float *__restrict__ xr, int64_t cnt, bool vec, CT b0, CT b1, CT b2, CT na1, CT na2, CT &s1,
+                                          CT &s2) {
+    auto step = [&](float xf) {
+        const CT v = static_cast<CT>(xf);
+        const CT y = fma_rn(b0, v, s1);
+        s1 = fma_rn(na1, y, fma_rn(b1, v, s2));
+        s2 = fma_rn(na2, y, b2 * v);
+    };
+    if (vec) {  // cnt is a multiple of 64 and the row piece is 16-byte aligned
+        const float4 *p4 = reinterpret_cast<const float4 *>(xr);
+        const int64_t n4 = cnt >> 2;
+        float4 u0 = n4 > 0 ? __ldg(p4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 u1 = n4 > 1 ? __ldg(p4 + 1) : u0;
+        for (int64_t i = 0; i < n4; i += 2) {
+            const float4 a0 = u0, a1v = u1;
+            if (i + 2 < n4) {  // next pair first: the loads fly under eight dependent recurrence steps
+                u0 = __ldg(p4 + i + 2);
+                u1 = __ldg(p4 + i + 3);
+            }
+            step(a0.x);
+            step(a0.y);
+            step(a0.z);
+            step(a0.w);
+            step(a1v.x);
+            step(a1v.y);
+            step(a1v.z);
+            step(a1v.w);
+        }
+    } else {
+        for (int64_t i = 0; i < cnt; ++i) step(__ldg(xr + i));
+    }
+}
+
+constexpr int kWarm1Warps = 4;
+// Piece length for a window of W samples: an ODD multiple of 32 samples (128 bytes), so that the 32 lanes' stretches of
+// the row, one piece apart, fall into different L1 sets (a power-of-two stride maps them all to one), and >= W / 32.
+__host__ __device__ inline int64_t warm1_piece(int64_t W) {
+    int64_t m = (W + 32 * 32 - 1) / (32 * 32);
+    if (m < 1) m = 1;
+    if ((m & 1) == 0) ++m;
+    return m * 32;
+}
+__global__ void __launch_bounds__(kWarm1Warps * 32, 8) bank_warm1_kernel(const __grid_constant__ StackCoef<1> cd, const __grid_constant__ StackGeom g,
+                                                                        int64_t nitems) {
+    const int lane = threadIdx.x & 31;
+    const int64_t item = static_cast<int64_t>(blockIdx.x) * kWarm1Warps + (threadIdx.x >> 5);
+    if (item >= nitems) return;  // warp-uniform
+    // item = (segment j - 1, channel c, band b), b fastest: neighbouring warps read the same stretch of the same row
+    const int b = static_cast<int>(item % g.n_bands);
+    const int64_t r = item / g.n_bands;
+    const int64_t c = r % g.C;
+    const int64_t j = r / g.C + 1;
+    const int64_t n1 = j * g.Lseg;
+    const int64_t W = g.warm_b[b];
+    const int64_t Lp = warm1_piece(W);              // piece length, samples
+    const int nl = static_cast<int>((W + Lp - 1) / Lp);  // pieces (= active lanes) that cover the window, <= 32
+    const int64_t hi = n1 - lane * Lp, lo = hi - Lp;
+    const int64_t lo_c = max(lo, static_cast<int64_t>(0));
+    const bool empty = lane >= nl || hi <= 0;
+    const double b0 = cd.b0[b][0], b1 = cd.b1[b][0], b2 = cd.b2[b][0], a1 = cd.a1[b][0], a2 = cd.a2[b][0];
+    double z1 = 0.0, z2 = 0.0;
+    if (!empty) {
+        if (lo <= 0 && g.state_x != nullptr) {  // this piece contains sample 0: start from the caller's DF1 state
+            const int64_t o = (static_cast<int64_t>(g.band_id[b]) * g.C + c) * 2;
+            const double x1 = g.state_x[o], x2 = g.state_x[o + 1];
+            const double y1 = g.state_y[o], y2 = g.state_y[o + 1];
+            z1 = b1 * x1 + b2 * x2 - a1 * y1 - a2 * y2;
+            z2 = b2 * x1 - a2 * y1;
+        }
+        const float *xr = g.x + c * g.ldx + lo_c;
+        if ((g.f64_mask >> b) & 1u) {
+            warm1_run<double>(xr, hi - lo_c, g.vec_ok != 0, b0, b1, b2, -a1, -a2, z1, z2);
+        } else {
+            float s1 = static_cast<float>(z1), s2 = static_cast<float>(z2);
+            warm1_run<float>(xr, hi - lo_c, g.vec_ok != 0, static_cast<float>(b0), static_cast<float>(b1), static_cast<float>(b2),
+                             static_cast<float>(-a1), static_cast<float>(-a2), s1, s2);
+            z1 = static_cast<double>(s1);
+            z2 = static_cast<double>(s2);
+        }
+    }
+    // A^(lane * Lp): M = A^Lp by binary exponentiation (warp-uniform), then M^lane from M, M^2, M^4, M^8, M^16
+    M22 M{1.0, 0.0, 0.0, 1.0}, Q{-a1, 1.0, -a2, 0.0};
+    for (int64_t e = Lp; e > 0; e >>= 1) {
+        if (e & 1) M = mmul(M, Q);
+        Q = mmul(Q, Q);
+    }
+    M22 P{1.0, 0.0, 0.0, 1.0};
+    for (int bit = 0; bit < 5 && ((max(nl, 1) - 1) >> bit) != 0; ++bit) {  // warp-uniform trip count
+        if ((lane >> bit) & 1) P = mmul(P, M);
+        M = mmul(M, M);
+    }
+    double t1 = empty ? 0.0 : __fma_rn(P.a, z1, P.b * z2);
+    double t2 = empty ? 0.0 : __fma_rn(P.c, z1, P.d * z2);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        t1 += __shfl_xor_sync(0xffffffffu, t1, off);
+        t2 += __shfl_xor_sync(0xffffffffu, t2, off);
+    }
+    if (lane == 0) {
+        double *wsp = g.ws + (c * g.S + j);
+        wsp[(b * 2) * g.ws_stride] = t1;
+        wsp[(b * 2 + 1) * g.ws_stride] = t2;
+    }
+}
+
 template <int KB>
 int launch_stack_kb(const SosSection *sec, StackGeom g, const Segmentation &seg, cudaStream_t stream) {
     StackCoef<KB> cd;
@@ -824,10 +951,39 @@ int launch_stack_kb(const SosSection *sec, StackGeom g, const Segmentation &seg,
     const int smem = cta_bytes(g.W, g.bpw, KB);
     const int64_t G = (g.C + 31) / 32;
     if (seg.S > 1) {
-        StackGeom gw = g;
-        gw.warm = seg.warm;
-        kern<<<static_cast<unsigned>(G * (seg.S - 1) * g.nsplit), g.W * 32, smem, stream>>>(cd, gw);
-        TFX_CHECK_LAUNCH("bank_stack_kernel(warm-up)");
+        static const bool serial_warm = std::getenv("TFX_BS_SERIAL_WARM") != nullptr;  // developer A/B switch
+        // Serial warm-up: one wave of CTAs, its time is the longest band's window (a single dependency chain).  Time-
+        // parallel warm-up: (nearly) the same arithmetic spread over all SMs, its time is the total work.  Both sustain
+        // ~0.9 G lane-samples per ms on a B200 (32 x 32 x 60 s: 1.08 ms serial, 0.5 ms parallel; 32 x 256 x 60 s: 1.6 ms
+        // against 2.7 ms), the serial chain runs ~35 ns per sample: take the parallel kernel while
+        // total / longest < ~30 000 concurrent lane-streams.
+        bool parallel_warm = false;
+        if constexpr (KB == 1) {
+            int64_t total = 0, longest = 1;
+            for (int b = 0; b < g.n_bands; ++b) {
+                const int64_t W = g.warm_b[b], Lp = warm1_piece(W);
+                total += (W + Lp - 1) / Lp * Lp;
+                longest = std::max<int64_t>(longest, W);
+            }
+            static const char *force = std::getenv("TFX_BS_PARALLEL_WARM");  // developer A/B switch
+            // (SUM banks run a single band split, so a warp's serial chain is the sum of its bands' windows: twice the room;
+            //  32 biquads x 256 ch x 60 s: 9.25 ms serial, 8.80 ms parallel)
+            parallel_warm = !serial_warm && (force != nullptr || static_cast<double>(g.C) * (seg.S - 1) * total / longest < (g.sum ? 60000.0 : 30000.0));
+        }
+        if constexpr (KB == 1) {
+            if (parallel_warm) {
+                const int64_t nitems = g.C * (seg.S - 1) * g.n_bands;
+                TFX_REQUIRE((nitems + kWarm1Warps - 1) / kWarm1Warps < (int64_t(1) << 31), "filterbank: too many warm-up items for one launch");
+                bank_warm1_kernel<<<static_cast<unsigned>((nitems + kWarm1Warps - 1) / kWarm1Warps), kWarm1Warps * 32, 0, stream>>>(cd, g, nitems);
+                TFX_CHECK_LAUNCH("bank_warm1_kernel");
+            }
+        }
+        if (!parallel_warm) {
+            StackGeom gw = g;
+            gw.warm = seg.warm;
+            kern<<<static_cast<unsigned>(G * (seg.S - 1) * g.nsplit), g.W * 32, smem, stream>>>(cd, gw);
+            TFX_CHECK_LAUNCH("bank_stack_kernel(warm-up)");
+        }
     }
     g.warm = 0;
     kern<<<static_cast<unsigned>(G * seg.S * g.nsplit), g.W * 32, smem, stream>>>(cd, g);
@@ -879,6 +1035,55 @@ bool bank_stack_tile_ok(int N, int Kb, int64_t C) {
 int launch_bank_stack(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int64_t ldy, int64_t ldb, const SosSection *sec,
                       const int *band_id, const int64_t *warm_b, uint32_t f64_mask, int nb, int Kb, bool sum, bool no_split,
                       void *workspace, size_t workspace_bytes, double *state_x, double *state_y, cudaStream_t stream) {
+    // Band splits (STACK over few channels): a CTA takes the local bands [s * bps, (s + 1) * bps).  In the caller's order
+    // (ascending frequency for a LogFilterBank) split 0 would hold all the long-warm-up, float64 bands and the grid --
+    // a single wave of CTAs -- would wait for it: the 32-channel shard of config 5 ran 2.87 ms with SM active cycles
+    // between 2.9 M and 5.5 M (profiles/r2_ncu_summary.md).  Deal the bands to the splits round-robin in order of cost
+    // instead (float64 first, then longer warm-up); band_id keeps the output planes and state blocks where they belong.
+    std::vector<SosSection> sec_p;
+    int band_id_p[32];
+    int64_t warm_p[32];
+    {
+        int64_t wm = 0;
+        bool ns_local = no_split;
+        for (int b = 0; b < nb; ++b) {
+            if (warm_b[b] < 0) ns_local = true;
+            wm = std::max<int64_t>(wm, warm_b[b] < 0 ? 0 : (warm_b[b] + kCH - 1) / kCH * kCH);
+        }
+        if (wm > (int64_t(1) << 30)) ns_local = true;
+        const StackPlan pl0 = plan_stack(C, T, nb, Kb, wm, sum, ns_local);
+        if (!sum && pl0.nsplit > 1) {
+            std::vector<int> order(nb);
+            for (int b = 0; b < nb; ++b) order[b] = b;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+                const int fa = (f64_mask >> a) & 1u, fb = (f64_mask >> b) & 1u;
+                if (fa != fb) return fa > fb;
+                return warm_b[a] > warm_b[b];
+            });
+            int filled[4] = {0, 0, 0, 0}, cap[4] = {0, 0, 0, 0};
+            for (int sp = 0; sp < pl0.nsplit; ++sp) cap[sp] = std::max(0, std::min(pl0.bps, nb - sp * pl0.bps));
+            int perm[32];  // perm[new local position] = caller's band
+            int sp = 0;
+            for (int t = 0; t < nb; ++t) {
+                while (filled[sp] >= cap[sp]) sp = (sp + 1) % pl0.nsplit;
+                perm[sp * pl0.bps + filled[sp]++] = order[t];
+                sp = (sp + 1) % pl0.nsplit;
+            }
+            sec_p.resize(static_cast<size_t>(nb) * Kb);
+            uint32_t mask_p = 0;
+            for (int q = 0; q < nb; ++q) {
+                const int o = perm[q];
+                for (int k = 0; k < Kb; ++k) sec_p[static_cast<size_t>(q) * Kb + k] = sec[static_cast<size_t>(o) * Kb + k];
+                band_id_p[q] = band_id[o];
+                warm_p[q] = warm_b[o];
+                mask_p |= ((f64_mask >> o) & 1u) << q;
+            }
+            sec = sec_p.data();
+            band_id = band_id_p;
+            warm_b = warm_p;
+            f64_mask = mask_p;
+        }
+    }
     StackGeom g{};
     g.sum = sum ? 1 : 0;
     g.x = x;
