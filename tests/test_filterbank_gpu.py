@@ -415,3 +415,54 @@ def test_stack_band_split_over_ctas(C, T):
     y2 = other(x)
     err = ((y2 - y).abs().amax(dim=(1, 2)) / y.abs().amax(dim=(1, 2))).max().item()
     assert err < 5e-6
+
+
+@pytest.mark.parametrize("mode", ["stack", "sum"])
+@pytest.mark.parametrize("C,T", [(32, 500000), (5, 300001)])
+def test_time_parallel_warm_up_matches_serial_and_oracle(mode, C, T, monkeypatch):
+    """Banks of single-section bands: the warm-up launch that prepares the segment start states is either serial (one
+    dependency chain per band window) or time-parallel (bank_warm1_kernel: 32 zero-state pieces per window combined with
+    powers of the free-response matrix).  Both forced (TFX_BS_SERIAL_WARM / TFX_BS_PARALLEL_WARM) on a LogFilterBank whose
+    20 Hz band's window (31 k samples) is longer than the first segments, so early pieces are truncated at sample 0 and
+    start from the carried DF1 state; fed in two chunks.  Oracle parity on every channel kept, and the two agree."""
+    from torchfx_b200.filter._sosbank import SosBank
+
+    g = torch.Generator(device=DEV).manual_seed(C + T)
+    x = 0.1 * torch.randn(C, T, device=DEV, generator=g)
+    freqs = [20.0 * (1000.0 ** (i / 31.0)) for i in range(32)]
+    mk = lambda: [fx.filter.BiquadBPF(f, 1.414, 48000) for f in freqs]
+    outs = {}
+    for name, env in (("serial", "TFX_BS_SERIAL_WARM"), ("parallel", "TFX_BS_PARALLEL_WARM")):
+        monkeypatch.delenv("TFX_BS_SERIAL_WARM", raising=False)
+        monkeypatch.delenv("TFX_BS_PARALLEL_WARM", raising=False)
+        monkeypatch.setenv(env, "1")
+        filters = mk()
+        bank = SosBank(filters, mode=mode)
+        bank.flags = _native.TFX_FORCE_TILE
+        cut = 100032 if C == 32 else 77777
+        before = _native.kernel_launches()
+        y = torch.cat([bank(x[:, :cut]), bank(x[:, cut:])], dim=-1)
+        assert 3 <= _native.kernel_launches() - before <= 4  # (warm-up + main) per chunk; a short chunk may run unsplit
+        outs[name] = (y, [f._state_y.clone() for f in filters])
+    sel = [0, C // 2, C - 1]
+    sos = np.stack([f._sos.numpy() for f in mk_computed(mk())])
+    xs = x[sel].cpu().numpy()
+    want = oracle.filterbank_stack(xs, sos)
+    if mode == "sum":
+        want = want.sum(axis=0)
+    for name, (y, _) in outs.items():
+        got = (y[:, sel] if mode == "stack" else y[sel]).cpu().numpy()
+        if mode == "stack":
+            assert max(rel_to_max(got[b], want[b]) for b in range(32)) < TOL, name
+        else:
+            assert rel_to_max(got, want) < TOL, name
+    ys, yp = outs["serial"][0], outs["parallel"][0]
+    assert float((ys - yp).abs().max() / ys.abs().max()) < 2e-6
+    for a, b in zip(outs["serial"][1], outs["parallel"][1]):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=1e-6 * float(a.abs().max()))
+
+
+def mk_computed(filters):
+    for f in filters:
+        f.compute_coefficients()
+    return filters

@@ -951,7 +951,7 @@ int launch_stack_kb(const SosSection *sec, StackGeom g, const Segmentation &seg,
     const int smem = cta_bytes(g.W, g.bpw, KB);
     const int64_t G = (g.C + 31) / 32;
     if (seg.S > 1) {
-        static const bool serial_warm = std::getenv("TFX_BS_SERIAL_WARM") != nullptr;  // developer A/B switch
+        const bool serial_warm = std::getenv("TFX_BS_SERIAL_WARM") != nullptr;  // developer A/B switch (read per call: tests toggle it)
         // Serial warm-up: one wave of CTAs, its time is the longest band's window (a single dependency chain).  Time-
         // parallel warm-up: (nearly) the same arithmetic spread over all SMs, its time is the total work.  Both sustain
         // ~0.9 G lane-samples per ms on a B200 (32 x 32 x 60 s: 1.08 ms serial, 0.5 ms parallel; 32 x 256 x 60 s: 1.6 ms
@@ -965,7 +965,7 @@ int launch_stack_kb(const SosSection *sec, StackGeom g, const Segmentation &seg,
                 total += (W + Lp - 1) / Lp * Lp;
                 longest = std::max<int64_t>(longest, W);
             }
-            static const char *force = std::getenv("TFX_BS_PARALLEL_WARM");  // developer A/B switch
+            const char *force = std::getenv("TFX_BS_PARALLEL_WARM");  // developer A/B switch
             // (SUM banks run a single band split, so a warp's serial chain is the sum of its bands' windows: twice the room;
             //  32 biquads x 256 ch x 60 s: 9.25 ms serial, 8.80 ms parallel)
             parallel_warm = !serial_warm && (force != nullptr || static_cast<double>(g.C) * (seg.S - 1) * total / longest < (g.sum ? 60000.0 : 30000.0));
