@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <list>
@@ -333,7 +334,15 @@ Segmentation choose_segmentation(int64_t C, int64_t T, int64_t warm_needed, int6
             const int v = e ? std::atoi(e) : 0;
             return static_cast<int64_t>(v >= 4 && v <= 1024 ? v : 32);
         }();
-        const int64_t fine = std::min<int64_t>(capacity / C * oversub, T / std::max<int64_t>(4096, kWarmDiv * warm));
+        // ... but never settle for a whole number of items per resident warp when the warm-up is long.  With config 4's
+        // mixed-precision chain (warm-up 1728 samples) the 1/kWarmDiv rule alone leaves ONE item per warp, and one or
+        // exactly two items per warp -- every warp starts and ends its items together with all the others -- measured
+        // 12-25 % slower than 1.7 items per warp on the same data (tools/cfg4_shard.py, 2048 / 1024 / 512 / 256 ch x 60 s:
+        // 8.3-9.0 / 5.0 / 2.56 / 1.36 ms at 1.0 or 2.0 items per warp, 8.3 / 4.4 / 2.26 / 1.22 ms at 1.7-2.3).  So: at least
+        // 1.73 items per warp as long as the warm-up stays <= 1/4 of a segment.
+        const int64_t by_warm = T / std::max<int64_t>(4096, kWarmDiv * warm);
+        const int64_t staggered = std::min<int64_t>((173 * capacity / C + 99) / 100, T / std::max<int64_t>(4096, 4 * warm));
+        const int64_t fine = std::min<int64_t>(capacity / C * oversub, std::max(by_warm, staggered));
         S = std::max(S, fine);
     }
     while (S >= 2) {
@@ -345,6 +354,7 @@ Segmentation choose_segmentation(int64_t C, int64_t T, int64_t warm_needed, int6
             g.S = S2;
             g.Lseg = L;
             g.warm = warm;
+            if (std::getenv("TFX_PLAN_DEBUG")) std::fprintf(stderr, "[tfx plan] C=%lld T=%lld warm=%lld capacity=%lld -> S=%lld Lseg=%lld\n", (long long)C, (long long)T, (long long)warm, (long long)capacity, (long long)g.S, (long long)g.Lseg);
             return g;
         }
         if (S2 < 2) break;
