@@ -827,86 +827,118 @@ struct M22 {
 __device__ __forceinline__ M22 mmul(const M22 &x, const M22 &y) {
     return M22{__fma_rn(x.a, y.a, x.b * y.c), __fma_rn(x.a, y.b, x.b * y.d), __fma_rn(x.c, y.a, x.d * y.c), __fma_rn(x.c, y.b, x.d * y.d)};
 }
-template <typename CT>
-__device__ __forceinline__ void warm1_run(const float *__restrict__ xr, int64_t cnt, bool vec, CT b0, CT b1, CT b2, CT na1, CT na2, CT &s1,
-                                          CT &s2) {
-    auto step = [&](float xf) {
-        const CT v = static_cast<CT>(xf);
-        const CT y = fma_rn(b0, v, s1);
-        s1 = fma_rn(na1, y, fma_rn(b1, v, s2));
-        s2 = fma_rn(na2, y, b2 * v);
-    };
-    if (vec) {  // cnt is a multiple of 64 and the row piece is 16-byte aligned
-        const float4 *p4 = reinterpret_cast<const float4 *>(xr);
-        const int64_t n4 = cnt >> 2;
-        float4 u0 = n4 > 0 ? __ldg(p4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 u1 = n4 > 1 ? __ldg(p4 + 1) : u0;
-        for (int64_t i = 0; i < n4; i += 2) {
-            const float4 a0 = u0, a1v = u1;
-            if (i + 2 < n4) {  // next pair first: the loads fly under eight dependent recurrence steps
-                u0 = __ldg(p4 + i + 2);
-                u1 = __ldg(p4 + i + 3);
-            }
-            step(a0.x);
-            step(a0.y);
-            step(a0.z);
-            step(a0.w);
-            step(a1v.x);
-            step(a1v.y);
-            step(a1v.z);
-            step(a1v.w);
-        }
-    } else {
-        for (int64_t i = 0; i < cnt; ++i) step(__ldg(xr + i));
-    }
-}
-
 constexpr int kWarm1Warps = 4;
-// Piece length for a window of W samples: an ODD multiple of 32 samples (128 bytes), so that the 32 lanes' stretches of
-// the row, one piece apart, fall into different L1 sets (a power-of-two stride maps them all to one), and >= W / 32.
+constexpr int kW1Samples = 32;                 // samples of every piece staged per step: 128-byte rows
+constexpr int kW1TileBytes = 32 * kW1Samples * 4;
+// Piece length for a window of W samples: an odd multiple of 32 samples (a whole number of staged tiles), >= W / 32.
 __host__ __device__ inline int64_t warm1_piece(int64_t W) {
     int64_t m = (W + 32 * 32 - 1) / (32 * 32);
     if (m < 1) m = 1;
     if ((m & 1) == 0) ++m;
     return m * 32;
 }
-__global__ void __launch_bounds__(kWarm1Warps * 32, 8) bank_warm1_kernel(const __grid_constant__ StackCoef<1> cd, const __grid_constant__ StackGeom g,
+// The warp stages tile i of all 32 pieces together -- [32 rows x 128 bytes], rows one piece apart in the channel's row --
+// with coalesced 16-byte cp.async (a warp instruction covers 4 rows x 128 bytes: 4 L1/L2 line requests), double buffered,
+// XOR-swizzled so that lane p reads "its" row with conflict-free 128-bit shared loads.  (A first version let every lane
+// load its own stretch straight from global memory: 32 line requests per warp instruction, and ncu showed the kernel
+// waiting on those loads -- long_scoreboard -- with the FP64 pipe 36 % busy.)
+template <typename CT>
+__device__ __forceinline__ void warm1_tile(const unsigned char *tile, int lane, CT b0, CT b1, CT b2, CT na1, CT na2, CT &s1, CT &s2) {
+    auto step = [&](float xf) {
+        const CT v = static_cast<CT>(xf);
+        const CT y = fma_rn(b0, v, s1);
+        s1 = fma_rn(na1, y, fma_rn(b1, v, s2));
+        s2 = fma_rn(na2, y, b2 * v);
+    };
+    const unsigned char *row = tile + lane * 128;
+    float4 a = *reinterpret_cast<const float4 *>(row + ((0 ^ (lane & 7)) << 4));
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        const int vn = (v + 1) & 7;
+        const float4 nxt = *reinterpret_cast<const float4 *>(row + ((vn ^ (lane & 7)) << 4));
+        step(a.x);
+        step(a.y);
+        step(a.z);
+        step(a.w);
+        a = nxt;
+    }
+}
+
+__global__ void __launch_bounds__(kWarm1Warps * 32, 7) bank_warm1_kernel(const __grid_constant__ StackCoef<1> cd, const __grid_constant__ StackGeom g,
                                                                         int64_t nitems) {
+    __shared__ __align__(128) unsigned char w1_smem[kWarm1Warps][2][kW1TileBytes];
     const int lane = threadIdx.x & 31;
     const int64_t item = static_cast<int64_t>(blockIdx.x) * kWarm1Warps + (threadIdx.x >> 5);
-    if (item >= nitems) return;  // warp-uniform
-    // item = (segment j - 1, channel c, band b), b fastest: neighbouring warps read the same stretch of the same row
-    const int b = static_cast<int>(item % g.n_bands);
-    const int64_t r = item / g.n_bands;
-    const int64_t c = r % g.C;
-    const int64_t j = r / g.C + 1;
+    if (item >= nitems) return;  // warp-uniform (no CTA barriers below)
+    unsigned char *buf = &w1_smem[threadIdx.x >> 5][0][0];
+    // item = (segment j - 1, band b, channel c), c fastest: the warps of a CTA run the SAME band on neighbouring channels, so
+    // they finish together (with b fastest a CTA held a 992-sample and three short pieces: ncu showed 36 % of the warp slots
+    // active); the bands of one segment follow each other, so their overlapping windows are served by L2.
+    const int64_t c = item % g.C;
+    const int64_t r = item / g.C;
+    const int b = static_cast<int>(r % g.n_bands);
+    const int64_t j = r / g.n_bands + 1;
     const int64_t n1 = j * g.Lseg;
     const int64_t W = g.warm_b[b];
-    const int64_t Lp = warm1_piece(W);              // piece length, samples
+    const int64_t Lp = warm1_piece(W);                   // piece length, samples
     const int nl = static_cast<int>((W + Lp - 1) / Lp);  // pieces (= active lanes) that cover the window, <= 32
-    const int64_t hi = n1 - lane * Lp, lo = hi - Lp;
-    const int64_t lo_c = max(lo, static_cast<int64_t>(0));
+    const int64_t ntiles = Lp / kW1Samples;
+    const int64_t hi = n1 - lane * Lp, lo = hi - Lp;     // my piece; samples before 0 do not exist
     const bool empty = lane >= nl || hi <= 0;
     const double b0 = cd.b0[b][0], b1 = cd.b1[b][0], b2 = cd.b2[b][0], a1 = cd.a1[b][0], a2 = cd.a2[b][0];
-    double z1 = 0.0, z2 = 0.0;
-    if (!empty) {
-        if (lo <= 0 && g.state_x != nullptr) {  // this piece contains sample 0: start from the caller's DF1 state
-            const int64_t o = (static_cast<int64_t>(g.band_id[b]) * g.C + c) * 2;
-            const double x1 = g.state_x[o], x2 = g.state_x[o + 1];
-            const double y1 = g.state_y[o], y2 = g.state_y[o + 1];
-            z1 = b1 * x1 + b2 * x2 - a1 * y1 - a2 * y2;
-            z2 = b2 * x1 - a2 * y1;
-        }
-        const float *xr = g.x + c * g.ldx + lo_c;
-        if ((g.f64_mask >> b) & 1u) {
-            warm1_run<double>(xr, hi - lo_c, g.vec_ok != 0, b0, b1, b2, -a1, -a2, z1, z2);
+    const bool is64 = (g.f64_mask >> b) & 1u;
+    const float *xrow = g.x + c * g.ldx;
+
+    auto issue = [&](int64_t i, int stage) {
+        unsigned char *tile = buf + stage * kW1TileBytes;
+        if (g.vec_ok) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int rr = (lane >> 3) + 4 * t, col = lane & 7;
+                const int64_t n = n1 - static_cast<int64_t>(rr + 1) * Lp + i * kW1Samples;  // first sample of tile i of piece rr
+                if (rr < nl && n >= 0) cp_async<16>(tile + rr * 128 + ((col ^ (rr & 7)) << 4), xrow + n + col * 4);
+            }
         } else {
-            float s1 = static_cast<float>(z1), s2 = static_cast<float>(z2);
-            warm1_run<float>(xr, hi - lo_c, g.vec_ok != 0, static_cast<float>(b0), static_cast<float>(b1), static_cast<float>(b2),
-                             static_cast<float>(-a1), static_cast<float>(-a2), s1, s2);
-            z1 = static_cast<double>(s1);
-            z2 = static_cast<double>(s2);
+            for (int idx = lane; idx < 32 * kW1Samples; idx += 32) {
+                const int rr = idx / kW1Samples, e = idx % kW1Samples;
+                const int64_t n = n1 - static_cast<int64_t>(rr + 1) * Lp + i * kW1Samples;
+                if (rr < nl && n >= 0) cp_async<4>(tile + rr * 128 + (((e >> 2) ^ (rr & 7)) << 4) + (e & 3) * 4, xrow + n + e);
+            }
         }
+    };
+
+    double z1 = 0.0, z2 = 0.0;
+    float f1 = 0.f, f2 = 0.f;
+    issue(0, 0);
+    cp_async_commit();
+    for (int64_t i = 0; i < ntiles; ++i) {
+        if (i + 1 < ntiles) issue(i + 1, static_cast<int>((i + 1) & 1));
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        const int64_t n = lo + i * kW1Samples;  // first sample of my tile
+        if (!empty && n >= 0) {
+            if (n == 0 && g.state_x != nullptr) {  // my piece contains sample 0: start from the caller's DF1 state, not from zero
+                const int64_t o = (static_cast<int64_t>(g.band_id[b]) * g.C + c) * 2;
+                const double x1 = g.state_x[o], x2 = g.state_x[o + 1];
+                const double y1 = g.state_y[o], y2 = g.state_y[o + 1];
+                z1 = b1 * x1 + b2 * x2 - a1 * y1 - a2 * y2;
+                z2 = b2 * x1 - a2 * y1;
+                f1 = static_cast<float>(z1);
+                f2 = static_cast<float>(z2);
+            }
+            const unsigned char *tile = buf + static_cast<int>(i & 1) * kW1TileBytes;
+            if (is64)
+                warm1_tile<double>(tile, lane, b0, b1, b2, -a1, -a2, z1, z2);
+            else
+                warm1_tile<float>(tile, lane, static_cast<float>(b0), static_cast<float>(b1), static_cast<float>(b2), static_cast<float>(-a1),
+                                  static_cast<float>(-a2), f1, f2);
+        }
+        __syncwarp();  // everyone is done with this stage before the copy of tile i + 2 lands in it
+    }
+    if (!is64) {
+        z1 = static_cast<double>(f1);
+        z2 = static_cast<double>(f2);
     }
     // A^(lane * Lp): M = A^Lp by binary exponentiation (warp-uniform), then M^lane from M, M^2, M^4, M^8, M^16
     M22 M{1.0, 0.0, 0.0, 1.0}, Q{-a1, 1.0, -a2, 0.0};
