@@ -13,3 +13,6 @@ OS_MODE=sum OS_N=32 OS_C=256 OS_T=2880000 OS_PREC=f32 timeout 400 $NCU -k regex:
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/r2_bench_launches.csv python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-secondary > $out/r2n_benchncu.log 2>&1
 for w in delay fir_direct fir_f64 bank_stream mixed6; do OS_WHAT=$w timeout 200 python tools/misc_once.py; done > $out/r2n_misc_times.log 2>&1
 ls -la $out/r2_*.ncu-rep
+# added at the end of round 2: the 32-channel STACK shard after the band dealing, and the time-parallel warm-up kernel
+OS_MODE=stack OS_C=32 OS_T=2880000 OS_PREC=auto timeout 400 $NCU -k regex:bank_stack_kernel --launch-skip 1 -o $out/r2_stack32ch_b -f python tools/bank_once.py > $out/r2n_stack32b.log 2>&1
+OS_MODE=stack OS_C=32 OS_T=2880000 OS_PREC=auto timeout 400 $NCU -k regex:bank_warm1_kernel --launch-skip 1 -o $out/r2_warm1_32ch_c -f python tools/bank_once.py > $out/r2n_warm1.log 2>&1
