@@ -126,9 +126,17 @@ __global__ void __launch_bounds__(256) fir_direct_f64_kernel(const double *__res
     }
 }
 
-int pick_algo(int algo, int64_t K) {
+// TFX_FIR_AUTO.  The single-partition overlap-save path costs the same for every K <= 1024 (256 ch x 60 s: 4.2 ms), the direct
+// form grows with K (2.7 / 3.3 / 4.3 / 5.6 / 7.0 / 9.7 ms at 8 / 16 / 32 / 48 / 64 / 96 taps) but has no fixed cost on small
+// inputs (8 ch x 10 s: 0.05-0.09 ms against 0.10): direct up to 32 taps, and up to 96 taps below 16 M samples
+// (tools/fir_direct_vs_ols.py).
+constexpr int kAutoDirectTapsLarge = 32;
+constexpr int64_t kAutoLargeSamples = int64_t(1) << 24;
+int pick_algo(int algo, int64_t K, int64_t C, int64_t T) {
     if (algo == TFX_FIR_DIRECT || algo == TFX_FIR_OLS) return algo;
-    return K <= kAutoDirectTaps ? TFX_FIR_DIRECT : TFX_FIR_OLS;
+    if (K <= kAutoDirectTapsLarge) return TFX_FIR_DIRECT;
+    if (K <= kAutoDirectTaps && C * T < kAutoLargeSamples) return TFX_FIR_DIRECT;
+    return TFX_FIR_OLS;
 }
 
 }  // namespace
@@ -138,7 +146,7 @@ extern "C" {
 
 size_t tfx_fir_workspace_bytes(int64_t C, int64_t T, int64_t K, int algo) {
     if (C <= 0 || T <= 0 || K <= 0) return 0;
-    if (tfx::pick_algo(algo, K) == TFX_FIR_DIRECT && K <= tfx::kDirectMaxTaps) return 0;
+    if (tfx::pick_algo(algo, K, C, T) == TFX_FIR_DIRECT && K <= tfx::kDirectMaxTaps) return 0;
     return tfx::fir_ols16k_workspace_bytes(K);
 }
 
@@ -154,7 +162,7 @@ int tfx_fir_f32(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int
     int rc = require_device();
     if (rc != TFX_OK) return rc;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-    int use = pick_algo(algo, K);
+    int use = pick_algo(algo, K, C, T);
     if (use == TFX_FIR_DIRECT && K > kDirectMaxTaps) use = TFX_FIR_OLS;
 
     if (use == TFX_FIR_DIRECT) {

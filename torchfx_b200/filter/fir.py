@@ -26,7 +26,9 @@ from ._base import AbstractFilter
 _ALGO = {"fft": N.TFX_FIR_AUTO, "auto": N.TFX_FIR_AUTO, "direct": N.TFX_FIR_DIRECT}
 
 
-_DIRECT_MAX_TAPS = 96  # TFX_FIR_AUTO takes the direct form up to here (csrc/fir.cu kAutoDirectTaps)
+def _auto_takes_overlap_save(K: int, samples: int) -> bool:
+    """TFX_FIR_AUTO's rule (csrc/fir.cu pick_algo): direct form up to 32 taps, and up to 96 taps below 16 M samples."""
+    return K > 96 or (K > 32 and samples >= 1 << 24)
 
 
 def fir_plan(taps: Tensor) -> Tensor:
@@ -119,7 +121,7 @@ class FIR(AbstractFilter):
         algo = _ALGO[self._conv_mode]
         plan = None
         K = taps.numel()
-        if x2.is_cuda and x2.dtype != torch.float64 and x2.numel() > 0 and (K > 1024 or (algo == N.TFX_FIR_AUTO and K > _DIRECT_MAX_TAPS)):
+        if x2.is_cuda and x2.dtype != torch.float64 and x2.numel() > 0 and (K > 1024 or (algo == N.TFX_FIR_AUTO and _auto_takes_overlap_save(K, x2.numel()))):
             # the overlap-save kernel will run: reuse the taps' spectra across calls (chunked callers); keyed by the
             # buffer's identity and version, so load_state_dict / in-place edits / .to() rebuild it
             key = (self.kernel.data_ptr(), self.kernel._version, K, x2.device)
