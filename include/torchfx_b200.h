@@ -119,6 +119,15 @@ int tfx_sos_cascade_f64(const double *x, double *y, int64_t C, int64_t T,
                         uint32_t flags, void *workspace, size_t workspace_bytes,
                         void *stream);
 
+/* The planner's time segmentation for `lanes` streams of T samples whose filter needs `warm_needed`
+ * warm-up samples (negative: never forgets -> no split) on a GPU that holds `capacity` streams in one
+ * wave, `oversub` work items per resident warp wanted (1 = static partition).  Pure host arithmetic
+ * (sos_plan.cpp); exported so that tests and integrators can see what a call will do without a
+ * device (TFX_PLAN_DEBUG=1 prints the same numbers for live calls).  Outputs: segments per
+ * channel, segment length (a multiple of 64 when split), warm-up length (multiple of 64).         */
+void tfx_plan_segmentation(int64_t lanes, int64_t T, int64_t warm_needed, int64_t capacity, int oversub,
+                           int64_t *segments, int64_t *segment_len, int64_t *warm);
+
 /* What TFX_PREC_AUTO resolves to for this cascade: returns TFX_PREC_F32 or TFX_PREC_F64,
  * and (optionally) the probe's estimated f32 round-off relative to max|y|.               */
 int tfx_sos_auto_precision(const double *sos_host, int K, double *probe_rel_err);

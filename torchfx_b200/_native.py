@@ -51,6 +51,7 @@ _SIGNATURES = {
     "tfx_filterbank_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
     "tfx_filterbank_f32": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, _P, c_int, c_int, c_int, _P, _P, c_uint32, _P, c_size_t, _P]),
     "tfx_filterbank_f64": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, c_int64, _P, c_int, c_int, c_int, _P, _P, c_uint32, _P, c_size_t, _P]),
+    "tfx_plan_segmentation": (None, [c_int64, c_int64, c_int64, c_int64, c_int, _P, _P, _P]),
     "tfx_fir_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
     "tfx_fir_f32": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64, c_int, _P, c_size_t, _P]),
     "tfx_fir_f64": (c_int, [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, c_int64, _P]),

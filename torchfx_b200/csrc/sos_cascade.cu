@@ -537,6 +537,14 @@ uint64_t tfx_sos_mixed_mask(const double *sos_host, int K, double *mixed_rel_err
     return plan->auto_prec == TFX_PREC_F64 ? plan->mixed_mask : 0;
 }
 
+void tfx_plan_segmentation(int64_t lanes, int64_t T, int64_t warm_needed, int64_t capacity, int oversub, int64_t *segments,
+                           int64_t *segment_len, int64_t *warm) {
+    const tfx::Segmentation g = tfx::choose_segmentation(lanes, T, warm_needed, capacity, false, oversub < 1 ? 1 : oversub);
+    if (segments) *segments = g.S;
+    if (segment_len) *segment_len = g.Lseg;
+    if (warm) *warm = g.warm;
+}
+
 int tfx_sos_auto_precision(const double *sos_host, int K, double *probe_rel_err) {
     auto plan = tfx::get_sos_plan(sos_host, K);
     if (!plan) return TFX_EINVAL;
