@@ -195,3 +195,17 @@ def test_float64_signals_are_filtered_in_float64(K, T, C):
     y2 = f(torch.from_numpy(x).to(DEV))
     assert y2.dtype == torch.float64
     assert rel_to_max(y2.cpu().numpy(), sps.lfilter(b.astype(np.float32).astype(np.float64), [1.0], x, axis=-1)) < 1e-12
+
+
+@pytest.mark.parametrize("K", [33, 97, 1024, 1025, 1026, 2048, 2049, 5000, 7168, 7169, 8191, 8192])
+@pytest.mark.parametrize("C,T", [(3, 2 * 15360 + 7), (2, 40001), (1, 9000)])
+def test_single_partition_hop_boundaries(K, C, T):
+    """K <= 8192 runs without a frequency-domain delay line, and its blocks hop by the largest multiple of 1024 that is
+    <= 16384 - K + 1 (15 360 samples up to 1025 taps, 14 336 from 1026, ..., 8192 from 7170): tap counts on both sides of
+    every kind of boundary, signals that end inside a block, one that is shorter than a block, an odd channel count."""
+    rng = np.random.default_rng(K * 7 + T)
+    x = rng.standard_normal((C, T)).astype(np.float32)
+    b = (rng.standard_normal(K) * np.exp(-np.arange(K) / (K / 4.0))).astype(np.float32)
+    want = oracle.fir_causal(x, b)
+    y = fir_causal(torch.from_numpy(x).to(DEV), torch.from_numpy(b), _native.TFX_FIR_OLS)
+    assert rel_to_max(y.cpu().numpy(), want) < TOL
