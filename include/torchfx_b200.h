@@ -80,7 +80,7 @@ extern "C" {
 #define TFX_BANK_SUM    1 /* y[c, t] = sum_b -- ParallelFilterCombination (__base.py:1019-1026) */
 
 /* FIR algorithm selection */
-#define TFX_FIR_AUTO    0 /* direct up to 32 taps, and up to 96 taps below 16 M samples; else OLS     */
+#define TFX_FIR_AUTO    0 /* direct up to 56 taps, and up to 96 taps below 16 M samples; else OLS     */
 #define TFX_FIR_DIRECT  1 /* shared-memory tiled direct form                                  */
 #define TFX_FIR_OLS     2 /* (partitioned) overlap-save block FFT in shared memory            */
 

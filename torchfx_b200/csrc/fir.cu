@@ -35,12 +35,17 @@ constexpr int kAutoDirectTaps = 96;
 // ------------------------------------------------------------------------------------------
 constexpr int kDirTile = 2048;  // outputs per CTA (256 threads x 8)
 
+// Shared-memory index of sample i of the tile: one pad word per 32, so that the threads' windows -- 8 samples apart, i.e.
+// 8 words apart: an 8-way bank conflict on every load of the main loop without the pad (ncu: mio_throttle) -- fall into
+// 32 different banks, and the cooperative fill (consecutive i) stays conflict-free.
+__device__ __forceinline__ int dpad(int i) { return i + (i >> 5); }
+
 __global__ void __launch_bounds__(256) fir_direct_kernel(const float *__restrict__ x, float *__restrict__ y, int64_t C,
                                                          int64_t T, int64_t ldx, int64_t ldy,
-                                                         const float *__restrict__ taps, int K, int64_t tiles_per_row) {
+                                                         const float *__restrict__ taps, int K, int64_t tiles_per_row, int vec_ok) {
     extern __shared__ float sm[];
     float *bs = sm;                  // K taps
-    float *xs = sm + ((K + 3) & ~3);  // K-1 history + kDirTile samples
+    float *xs = sm + ((K + 3) & ~3);  // K-1 history + kDirTile samples, padded (dpad)
     const int64_t c = blockIdx.x / tiles_per_row;
     const int64_t n0 = (blockIdx.x - c * tiles_per_row) * kDirTile;
     const float *xr = x + c * ldx;
@@ -48,7 +53,7 @@ __global__ void __launch_bounds__(256) fir_direct_kernel(const float *__restrict
     const int span = kDirTile + K - 1;
     for (int i = threadIdx.x; i < span; i += 256) {
         const int64_t n = n0 - (K - 1) + i;
-        xs[i] = (n >= 0 && n < T) ? xr[n] : 0.f;
+        xs[dpad(i)] = (n >= 0 && n < T) ? xr[n] : 0.f;
     }
     __syncthreads();
     // outputs n0 + 8t + r, r = 0..7:  y = sum_j b[j] * xs[(K-1) + 8t + r - j]
@@ -56,8 +61,8 @@ __global__ void __launch_bounds__(256) fir_direct_kernel(const float *__restrict
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float w[8];  // w[(m) & 7] holds xs[(K-1) + t8 + m - j] for the current j, m = 0..7
 #pragma unroll
-    for (int m = 0; m < 8; ++m) w[m] = xs[(K - 1) + t8 + m];
-    const float *xnew = xs + (K - 1) + t8 - 1;  // element entering the window after tap j: xnew[-j]
+    for (int m = 0; m < 8; ++m) w[m] = xs[dpad((K - 1) + t8 + m)];
+    const int inew = (K - 1) + t8 - 1;  // element entering the window after tap j: sample inew - j
     int j = 0;
     for (; j + 8 <= K; j += 8) {
 #pragma unroll
@@ -66,19 +71,26 @@ __global__ void __launch_bounds__(256) fir_direct_kernel(const float *__restrict
             // window for tap j+u: output r uses xs[.. + r - (j+u)] = w[(r - u) & 7]
 #pragma unroll
             for (int r = 0; r < 8; ++r) acc[r] = fmaf(b, w[(r - u) & 7], acc[r]);
-            w[(7 - u) & 7] = xnew[-(j + u)];  // slot of r = 7 is free; it becomes r = 0 of the next tap
+            const int i = inew - (j + u);
+            w[(7 - u) & 7] = i >= 0 ? xs[dpad(i)] : 0.f;  // slot of r = 7 is free; it becomes r = 0 of the next tap (i < 0 only past the last tap)
         }
     }
     for (; j < K; ++j) {  // remainder (K % 8 taps), plain indexing
         const float b = bs[j];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) acc[r] = fmaf(b, xs[(K - 1) + t8 + r - j], acc[r]);
+        for (int r = 0; r < 8; ++r) acc[r] = fmaf(b, xs[dpad((K - 1) + t8 + r - j)], acc[r]);
     }
     float *yr = y + c * ldy;
+    const int64_t nb = n0 + t8;
+    if (vec_ok && nb + 8 <= T) {  // two 16-byte streaming stores instead of eight 4-byte ones
+        st_stream16(yr + nb, make_float4(acc[0], acc[1], acc[2], acc[3]));
+        st_stream16(yr + nb + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+    } else {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const int64_t n = n0 + t8 + r;
-        if (n < T) yr[n] = acc[r];
+        for (int r = 0; r < 8; ++r) {
+            const int64_t n = nb + r;
+            if (n < T) yr[n] = acc[r];
+        }
     }
 }
 
@@ -127,10 +139,10 @@ __global__ void __launch_bounds__(256) fir_direct_f64_kernel(const double *__res
 }
 
 // TFX_FIR_AUTO.  The single-partition overlap-save path costs the same for every K <= 1024 (256 ch x 60 s: 4.2 ms), the direct
-// form grows with K (2.7 / 3.3 / 4.3 / 5.6 / 7.0 / 9.7 ms at 8 / 16 / 32 / 48 / 64 / 96 taps) but has no fixed cost on small
-// inputs (8 ch x 10 s: 0.05-0.09 ms against 0.10): direct up to 32 taps, and up to 96 taps below 16 M samples
+// form grows with K (1.3 / 2.3 / 2.6 / 3.4 / 4.3 / 6.0 ms at 8 / 16 / 32 / 48 / 64 / 96 taps) but has no fixed cost on small
+// inputs (8 ch x 10 s: 0.05-0.09 ms against 0.10): direct up to 56 taps, and up to 96 taps below 16 M samples
 // (tools/fir_direct_vs_ols.py).
-constexpr int kAutoDirectTapsLarge = 32;
+constexpr int kAutoDirectTapsLarge = 56;
 constexpr int64_t kAutoLargeSamples = int64_t(1) << 24;
 int pick_algo(int algo, int64_t K, int64_t C, int64_t T) {
     if (algo == TFX_FIR_DIRECT || algo == TFX_FIR_OLS) return algo;
@@ -167,10 +179,12 @@ int tfx_fir_f32(const float *x, float *y, int64_t C, int64_t T, int64_t ldx, int
 
     if (use == TFX_FIR_DIRECT) {
         const int64_t tiles = (T + kDirTile - 1) / kDirTile;
-        const size_t smem = sizeof(float) * (((K + 3) & ~3) + kDirTile + K - 1);
+        const int64_t span = kDirTile + K - 1;
+        const size_t smem = sizeof(float) * (((K + 3) & ~3) + span + span / 32 + 1);
+        const int vec_ok = (reinterpret_cast<uintptr_t>(y) % 16 == 0 && ldy % 4 == 0) ? 1 : 0;
         TFX_REQUIRE(C * tiles < (int64_t(1) << 31), "fir: too many tiles for one launch");
         fir_direct_kernel<<<static_cast<unsigned>(C * tiles), 256, smem, stream>>>(x, y, C, T, ldx, ldy, taps, static_cast<int>(K),
-                                                                                 tiles);
+                                                                                 tiles, vec_ok);
         TFX_CHECK_LAUNCH("fir_direct_kernel");
         return TFX_OK;
     }

@@ -27,8 +27,8 @@ _ALGO = {"fft": N.TFX_FIR_AUTO, "auto": N.TFX_FIR_AUTO, "direct": N.TFX_FIR_DIRE
 
 
 def _auto_takes_overlap_save(K: int, samples: int) -> bool:
-    """TFX_FIR_AUTO's rule (csrc/fir.cu pick_algo): direct form up to 32 taps, and up to 96 taps below 16 M samples."""
-    return K > 96 or (K > 32 and samples >= 1 << 24)
+    """TFX_FIR_AUTO's rule (csrc/fir.cu pick_algo): direct form up to 56 taps, and up to 96 taps below 16 M samples."""
+    return K > 96 or (K > 56 and samples >= 1 << 24)
 
 
 def fir_plan(taps: Tensor) -> Tensor:
