@@ -101,11 +101,13 @@ __global__ void __launch_bounds__(256) fir_direct_kernel(const float *__restrict
 // O(K T): float64 audio on the device is the rare case, the float32 overlap-save path is the fast one.
 // ------------------------------------------------------------------------------------------
 constexpr int kD64Tile = 1024, kD64Chunk = 512;
+// one pad double per 16: the threads' windows are 4 doubles apart, which without the pad is a 4-way conflict per half-warp
+__device__ __forceinline__ int dpad64(int i) { return i + (i >> 4); }
 __global__ void __launch_bounds__(256) fir_direct_f64_kernel(const double *__restrict__ x, double *__restrict__ y, int64_t C, int64_t T,
                                                              int64_t ldx, int64_t ldy, const double *__restrict__ taps, int64_t K,
                                                              int64_t tiles_per_row) {
     __shared__ double bs[kD64Chunk];
-    __shared__ double xs[kD64Tile + kD64Chunk];
+    __shared__ double xs[kD64Tile + kD64Chunk + (kD64Tile + kD64Chunk) / 16 + 1];  // padded: one word per 16 (see dpad64)
     const int64_t c = blockIdx.x / tiles_per_row;
     const int64_t n0 = (blockIdx.x - c * tiles_per_row) * kD64Tile;
     const double *xr = x + c * ldx;
@@ -113,21 +115,29 @@ __global__ void __launch_bounds__(256) fir_direct_f64_kernel(const double *__res
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int64_t j0 = 0; j0 < K; j0 += kD64Chunk) {
         const int kc = static_cast<int>(min(static_cast<int64_t>(kD64Chunk), K - j0));
+        const int kc4 = (kc + 3) & ~3;  // taps of this chunk, zero-padded to a multiple of 4 (a 64-tap filter used to run all 512)
         __syncthreads();
         for (int i = threadIdx.x; i < kD64Chunk; i += 256) bs[i] = i < kc ? taps[j0 + i] : 0.0;
-        // xs[i] = x[n0 - j0 - (kD64Chunk - 1) + i]: the samples taps j0 .. j0 + 511 pair with outputs n0 .. n0 + 1023
+        // sample i of the tile = x[n0 - j0 - (kD64Chunk - 1) + i]: the samples taps j0 .. j0 + 511 pair with outputs n0 .. n0 + 1023
         for (int i = threadIdx.x; i < kD64Tile + kD64Chunk; i += 256) {
             const int64_t n = n0 - j0 - (kD64Chunk - 1) + i;
-            xs[i] = (n >= 0 && n < T) ? xr[n] : 0.0;
+            xs[dpad64(i)] = (n >= 0 && n < T) ? xr[n] : 0.0;
         }
         __syncthreads();
-        // output n0 + t4 + r, tap j0 + u: x[n0 + t4 + r - j0 - u] = xs[(kD64Chunk - 1) + t4 + r - u]
-        const double *w = xs + (kD64Chunk - 1) + t4;
-#pragma unroll 4
-        for (int u = 0; u < kD64Chunk; ++u) {
-            const double b = bs[u];
+        // output n0 + t4 + r, tap j0 + u: sample (kD64Chunk - 1) + t4 + r - u; a register window slides over the taps
+        const int base = (kD64Chunk - 1) + t4;
+        double w[4];  // w[(r - u) & 3] = sample base + r - u
 #pragma unroll
-            for (int r = 0; r < 4; ++r) acc[r] = fma(b, w[r - u], acc[r]);
+        for (int r = 0; r < 4; ++r) w[r] = xs[dpad64(base + r)];
+        for (int u = 0; u < kc4; u += 4) {
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) {
+                const double b = bs[u + uu];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[r] = fma(b, w[(r - uu) & 3], acc[r]);
+                const int i = base - 1 - (u + uu);
+                w[(3 - uu) & 3] = i >= 0 ? xs[dpad64(i)] : 0.0;  // the slot of r = 3 becomes r = 0 of the next tap
+            }
         }
     }
     double *yr = y + c * ldy;
