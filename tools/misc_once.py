@@ -13,7 +13,7 @@ if what == "delay":
     fn = lambda: fx.Reverb(delay=4410, decay=0.5, mix=0.5)(x)
 elif what == "fir_direct":
     x = torch.empty((256, 60 * FS), device="cuda").normal_(0, 0.1)
-    f = fx.filter.FIR(np.hanning(64).astype(np.float32))
+    f = fx.filter.FIR(np.hanning(64).astype(np.float32), conv_mode="direct")  # (AUTO takes overlap-save above 56 taps at this size)
     fn = lambda: f(x)
 elif what == "fir_f64":
     x = torch.empty((16, 10 * FS), device="cuda", dtype=torch.float64).normal_(0, 0.1)
