@@ -32,6 +32,7 @@ struct Staging {
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
     cudaEvent_t e_in[kBufs], e_k[kBufs], e_out[kBufs];
     bool init = false;
+    std::mutex mu;  // one streaming call at a time PER DEVICE (the staging buffers and streams are per device)
 };
 
 std::mutex g_mu;
@@ -116,8 +117,13 @@ extern "C" int tfx_sos_cascade_host_f32(const float *x_host, float *y_host, int6
     chunk_T = std::min(chunk_T, T);
     chunk_T = (chunk_T + 3) / 4 * 4;
 
-    std::lock_guard<std::mutex> lk(g_mu);  // one streaming call at a time per process
-    Staging &s = *staging_for(device);
+    Staging *sp = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);  // the registry only; calls on different devices run concurrently
+        sp = staging_for(device);
+    }
+    Staging &s = *sp;
+    std::lock_guard<std::mutex> lk(s.mu);
     const size_t state_elems = static_cast<size_t>(K) * C * 2;
     const size_t ws_bytes = tfx_sos_cascade_workspace_bytes(C, chunk_T, K);
     rc = ensure(s, static_cast<size_t>(C) * chunk_T, 2 * state_elems, ws_bytes);
