@@ -60,3 +60,21 @@ def test_round2_rules():
     assert plan(512, 2_880_000, 4480)[0] == CAP // 512
     S, _, _ = plan(1024, 2_880_000, 4480)
     assert 1.7 <= 1024 * S / CAP <= 1.8
+
+
+def test_fir_auto_rule_mirrored_in_python():
+    """filter/fir.py decides whether to build an overlap-save plan with the same rule csrc/fir.cu's TFX_FIR_AUTO uses;
+    tfx_fir_workspace_bytes is host arithmetic (0 bytes <=> the direct form runs), so the two are compared here on a grid."""
+    from torchfx_b200.filter.fir import _auto_takes_overlap_save
+
+    lib = _native.load()
+    for K in (1, 8, 32, 56, 57, 64, 96, 97, 300, 1024, 1025, 70000):
+        for C, T in ((1, 1000), (2, 48000), (8, 480000), (64, 262144), (64, 262145), (256, 2880000)):
+            ols = lib.tfx_fir_workspace_bytes(C, T, K, _native.TFX_FIR_AUTO) > 0
+            assert ols == _auto_takes_overlap_save(K, C * T), (K, C, T)
+    # forced modes: the direct form is kept up to 1024 taps, beyond that it is overlap-save whatever was asked
+    assert lib.tfx_fir_workspace_bytes(4, 10000, 1024, _native.TFX_FIR_DIRECT) == 0
+    assert lib.tfx_fir_workspace_bytes(4, 10000, 1025, _native.TFX_FIR_DIRECT) > 0
+    assert lib.tfx_fir_workspace_bytes(4, 10000, 8, _native.TFX_FIR_OLS) > 0
+    # the plan holds the twiddle tables and one 128 KB spectrum row per 8192-tap partition
+    assert lib.tfx_fir_plan_bytes(65536) - lib.tfx_fir_plan_bytes(8192) == 7 * 8192 * 16
