@@ -105,6 +105,9 @@ def test_plan_is_bit_identical_and_cached(K):
     f.kernel.mul_(2.0)
     yc = f(x)
     assert rel_to_max(yc.cpu().numpy(), 2.0 * y0.cpu().numpy()) < 1e-6
+    f.kernel = f.kernel * 0.25  # a REPLACED buffer (new tensor object, version 0): the plan must follow it too
+    yd = f(x)
+    assert rel_to_max(yd.cpu().numpy(), 0.5 * y0.cpu().numpy()) < 1e-6
 
 
 def test_cfg3_reverb_ir_65536_taps():

@@ -123,11 +123,12 @@ class FIR(AbstractFilter):
         K = taps.numel()
         if x2.is_cuda and x2.dtype != torch.float64 and x2.numel() > 0 and (K > 1024 or (algo == N.TFX_FIR_AUTO and _auto_takes_overlap_save(K, x2.numel()))):
             # the overlap-save kernel will run: reuse the taps' spectra across calls (chunked callers); keyed by the
-            # buffer's identity and version, so load_state_dict / in-place edits / .to() rebuild it
-            key = (self.kernel.data_ptr(), self.kernel._version, K, x2.device)
-            if self._plan_key != key:
+            # buffer's identity and version, so load_state_dict / in-place edits / .to() / a replaced buffer rebuild it
+            # (the tensor OBJECT is kept, not its address: an address can be reused by a new buffer with version 0)
+            src, ver, dev = self._plan_key if self._plan_key is not None else (None, -1, None)
+            if src is not self.kernel or ver != self.kernel._version or dev != x2.device:
                 self._plan = fir_plan(taps.to(x2.device))
-                self._plan_key = key
+                self._plan_key = (self.kernel, self.kernel._version, x2.device)
             plan = self._plan
         return fir_causal(x2, taps, algo, plan=plan).reshape(shape)
 
